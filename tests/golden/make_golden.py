@@ -1,0 +1,146 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REFERENCE ITSELF (oracle/_ref, built from
+/root/reference by oracle/make_ref.py) on seeded inputs.
+
+Run here (the container that has /root/reference):
+    python oracle/make_ref.py && python tests/golden/make_golden.py
+The .npz fixtures are committed; this script is committed so they can be regenerated.
+The reference modules used are its pure-Python fp64 path:
+    neighbour_list.VerletList.build            (neighbour_list.py:160-189)
+    neighbour_list.NeighbourList.separations   (neighbour_list.py:63-83, fp64, wrap-then-norm)
+    properties.spam_properties                 (properties.py:63-120)
+    forces.SpamForce / forces.Force.apply      (forces.py:38-42,321-368)
+    spkernel.lucy_kernel, properties.vdw*      (spkernel.py:86-118, properties.py:38-49)
+plus VerletList.compress / ponder_rebuild for the list-maintenance fixture.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+
+import forces            # noqa: E402
+import neighbour_list    # noqa: E402
+import particles         # noqa: E402
+import properties        # noqa: E402
+import spkernel          # noqa: E402
+
+
+def run_case(name, r, v, m, h, t, box, cutoff, tolerance, fcutoff=5.0):
+    n = r.shape[0]
+    p = particles.SmoothParticleSystem(n, d=3, maxn=n, xmax=box[0], ymax=box[1], zmax=box[2])
+    p.r[:, :] = r
+    p.v[:, :] = v
+    p.m[:] = m
+    p.h[:] = h
+    p.t[:] = t
+    nl = neighbour_list.VerletList(p, cutoff=cutoff, tolerance=tolerance)
+    nl.build()
+    k = nl.nip
+    rsq_build = nl.rsq[:k].copy()
+    neighbour_list.NeighbourList.separations(nl)        # fp64 consistent separations
+    properties.spam_properties(p, nl)
+    p.vdot[:, :] = 0.0
+    p.udot[:] = 0.0
+    f = forces.SpamForce(p, nl, cutoff=fcutoff)
+    f.apply()
+    out = dict(r=r, v=v, m=m, h=h, t_in=t, box=np.array(box, dtype=np.float64),
+               cutoff=cutoff, tolerance=tolerance, fcutoff=fcutoff,
+               iap=nl.iap[:k].astype(np.int32), rsq_build=rsq_build,
+               drij=nl.drij[:k].copy(), rij=nl.rij[:k].copy(), dv=nl.dv[:k].copy(),
+               wij=nl.wij[:k].copy(), dwij=nl.dwij[:k].copy(),
+               rho=p.rho.copy(), p=p.p.copy(), pco=p.pco.copy(), u=p.u.copy(), t_out=p.t.copy(),
+               vdot=p.vdot.copy(), udot=p.udot.copy())
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("%-22s n=%5d pairs=%6d  mean rho=%.6f  max|vdot|=%.4e" %
+          (name, n, k, p.rho.mean(), np.abs(p.vdot).max()))
+
+
+def lattice(nx, ny, nz, seed, jitter=0.1, vmax=0.1):
+    rng = np.random.default_rng(seed)
+    n = nx * ny * nz
+    idx = np.arange(n)
+    r = np.empty((n, 3))
+    r[:, 0] = idx % nx + 0.5
+    r[:, 1] = (idx // nx) % ny + 0.5
+    r[:, 2] = idx // (nx * ny) + 0.5
+    r += rng.uniform(-jitter, jitter, size=(n, 3))
+    v = vmax * (rng.random((n, 3)) - 0.5)
+    return r, v
+
+
+def main():
+    # -- known-answer values straight from the reference functions
+    kat = {}
+    for i, (r, dx, h) in enumerate([(0.0, (0., 0., 0.), 2.0), (0.0, (0., 0., 0.), 1.0),
+                                    (1.0, (1., 0., 0.), 2.0), (1.5, (0.9, 1.2, 0.), 2.0),
+                                    (1.0, (1., 0.), 2.0), (0.5, (0.5,), 2.0),
+                                    (2.0, (2., 0., 0.), 2.0), (2.5, (1.5, 2., 0.), 2.0),
+                                    (0.3, (0.1, -0.2, 0.2), 1.3)]):
+        w, dw = spkernel.lucy_kernel(r, dx, h)
+        dwa = np.zeros(3)
+        dwa[:len(dx)] = np.atleast_1d(np.asarray(dw, dtype=np.float64))
+        dxa = np.zeros(3)
+        dxa[:len(dx)] = dx
+        kat["lucy_%d" % i] = np.array([r, h, len(dx), dxa[0], dxa[1], dxa[2], w, dwa[0], dwa[1], dwa[2]])
+    kat["vdw_1_1"] = np.array(properties.vdw(1.0, 1.0))
+    kat["vdw_05_15"] = np.array(properties.vdw(0.5, 1.5))
+    kat["vdw_energy_1_5"] = np.array(properties.vdw_energy(1.0, 5.0))
+    kat["vdw_temp_1_3"] = np.array(properties.vdw_temp(1.0, 3.0))
+    np.savez_compressed(os.path.join(HERE, "kat.npz"), **kat)
+
+    # -- C1-style sheet: 20x20x1, box 20^3, default Verlet tolerance (SURVEY 8d "C1")
+    r, v = lattice(20, 20, 1, 20261)
+    n = r.shape[0]
+    run_case("sheet_400", r, v, np.ones(n), np.full(n, 2.0), np.ones(n), (20., 20., 20.), 2.0, 1.0)
+
+    # -- small periodic cube: only 2 cells per side -> exercises the degenerate-grid path
+    r, v = lattice(6, 6, 6, 20262)
+    n = r.shape[0]
+    run_case("cube_216", r, v, np.ones(n), np.full(n, 2.0), np.ones(n), (6., 6., 6.), 2.0, 1.0)
+
+    # -- periodic cube 9^3 with cutoff=h=2, tolerance 0 (the bench's physical setting)
+    r, v = lattice(9, 9, 9, 20263)
+    n = r.shape[0]
+    run_case("cube_729", r, v, np.ones(n), np.full(n, 2.0), np.ones(n), (9., 9., 9.), 2.0, 0.0)
+
+    # -- random gas: non-uniform m, h, t; anisotropic box; some particles outside [0,L]
+    rng = np.random.default_rng(20264)
+    n = 500
+    box = (11.0, 9.5, 7.25)
+    r = rng.random((n, 3)) * np.array(box)
+    r[:25] += rng.uniform(-1.5, 1.5, size=(25, 3))          # strays beyond the faces
+    r[25] = (0.0, 0.0, 0.0)
+    r[26] = (11.0, 9.5, 7.25)                               # exactly on the far corner
+    r[27] = r[28]                                           # coincident pair (r == 0)
+    v = rng.normal(size=(n, 3))
+    m = rng.uniform(0.5, 1.5, n)
+    h = rng.uniform(1.4, 2.2, n)
+    t = rng.uniform(0.5, 1.5, n)
+    run_case("gas_500", r, v, m, h, t, box, 2.0, 1.0, fcutoff=1.9)
+
+    # -- list maintenance: build -> move -> compress -> ponder_rebuild
+    r, v = lattice(7, 7, 7, 20265)
+    n = r.shape[0]
+    p = particles.SmoothParticleSystem(n, d=3, maxn=n, xmax=7., ymax=7., zmax=7.)
+    p.r[:, :] = r
+    p.v[:, :] = v
+    nl = neighbour_list.VerletList(p, cutoff=2.0, tolerance=0.5)
+    nl.build()
+    iap0 = nl.iap[:nl.nip].copy()
+    rng = np.random.default_rng(20266)
+    r1 = r + rng.uniform(-0.2, 0.2, size=r.shape)
+    p.r[:, :] = r1
+    nl.compress()
+    np.savez_compressed(os.path.join(HERE, "maintain_343.npz"), r0=r, r1=r1, v=v,
+                        box=np.array([7., 7., 7.]), cutoff=2.0, tolerance=0.5,
+                        iap_build=iap0.astype(np.int32), iap_compress=nl.iap[:nl.nip].astype(np.int32),
+                        rebuild=np.array(nl.rebuild_list))
+    print("maintain_343           build=%d compress=%d rebuild=%s" % (iap0.shape[0], nl.nip, nl.rebuild_list))
+
+
+if __name__ == "__main__":
+    main()
