@@ -1,0 +1,211 @@
+/* pyticles_b200 -- C ABI of the B200 (sm_100a) SPH step hot path.
+ *
+ * This is the drop-in boundary for pyticles' hot path.  The reference has no FFI of its
+ * own: the boundary there is Python duck typing, `import c_forces as forces`
+ * (run_scripts/ospana.py:13) / `import f_properties as properties` (particles.py:28), with
+ * Cython (`pairsep.pyx`, `c_forces.pyx`) and f2py modules behind it.  Each entry point
+ * below names the reference routine it replaces (file:line into the reference tree).
+ * INTEGRATION.md shows the ctypes stub a pyticles maintainer would add.
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes and POD structs only; no C++/torch types.
+ *   - Every pointer named d_* (and every pointer inside sph_buffers) is a DEVICE pointer
+ *     owned by the caller (the Python side allocates them as torch tensors); the library
+ *     never allocates or frees device memory and keeps no state between calls.
+ *   - `stream` is a cudaStream_t passed as void*.  All work is enqueued on it; no call
+ *     synchronises the device.  Results that the host needs (pair count, overflow,
+ *     rebuild decision) are left in the device-side `sph_status`, which the caller copies
+ *     back when it wants them.
+ *   - Return value: SPH_OK (0), or a negative SPH_E_* for bad arguments, or a positive
+ *     cudaError_t from the launch.  Nothing throws.
+ *   - Particle arrays keep pyticles' layout: r, v, vdot are C-order [n,3] float64;
+ *     m, h, t, rho, p, pco, u, udot are [n] float64 (particles.py:122-127,323-343).
+ */
+#ifndef PYTICLES_B200_H
+#define PYTICLES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPH_ABI_VERSION 1
+
+enum {
+    SPH_OK = 0,
+    SPH_E_BADARG = -1,    /* null pointer, n < 0, capacity <= 0, ... */
+    SPH_E_GRID = -2,      /* box / cutoff cannot be gridded (non-positive or non-finite) */
+    SPH_E_TOOBIG = -3     /* more cells or particles than 32-bit indices allow */
+};
+
+/* status flags (sph_status.flags) */
+enum {
+    SPH_F_NONFINITE = 1,      /* a position is NaN/Inf */
+    SPH_F_OUT_OF_RANGE = 2,   /* a position is outside [-L/4, 5L/4]: the fp32 pre-filter is
+                                 switched off and every candidate is tested in fp64 */
+    SPH_F_OUT_OF_BOX = 4,     /* a position is outside [0, L): interior cells keep the
+                                 minimum-image test */
+    SPH_F_NBR_OVERFLOW = 8,   /* some particle has more neighbours than `max_nbrs`;
+                                 sph_status.max_count says how many are needed */
+    SPH_F_OUT_OF_SLAB = 16    /* a particle lies outside the local cell-layer range */
+};
+
+/* Device-resident status block (64 bytes).  Zero it with sph_status_reset before a build. */
+typedef struct sph_status {
+    uint32_t flags;
+    uint32_t max_count;          /* largest per-particle neighbour count seen */
+    unsigned long long n_links;  /* sum of per-particle neighbour counts = 2 * nip */
+    unsigned long long n_exact;  /* candidates that needed the fp64 predicate */
+    unsigned long long dsq_max_bits; /* ponder_rebuild: max |r_old - r|^2 as ordered bits */
+    uint32_t rebuild;            /* ponder_rebuild result (neighbour_list.py:225-234) */
+    uint32_t reserved[7];
+} sph_status;
+
+/* Cell grid description (host POD, passed by pointer, copied into kernel arguments). */
+typedef struct sph_grid {
+    double box[3];       /* xmax, ymax, zmax   (box.py:19-23) */
+    double thr;          /* cutoff^2 + tolerance^2   (neighbour_list.py:155-157,178) */
+    double w[3];         /* cell width per dimension (>= sqrt(thr) * (1 + 2^-20)) */
+    double inv_w[3];     /* nc / box */
+    int32_t nc[3];       /* cells per dimension across the whole periodic box */
+    int32_t lo[3];       /* first global cell layer of the local grid (0 on one GPU) */
+    int32_t ncl[3];      /* local cell layers (== nc on one GPU) */
+    int32_t wrap[3];     /* 1: local grid is periodic in this dimension */
+    uint32_t mask[3];    /* bit positions of each dimension in the Morton cell code */
+    uint32_t ncode;      /* number of cell codes = 1 << (total bits) */
+    float thr_in;        /* fp32 pre-filter: rsq32 <  thr_in  => certainly inside  */
+    float thr_out;       /*                  rsq32 >= thr_out => certainly outside */
+    int32_t reserved[4];
+} sph_grid;
+
+/* Equation of state constants (properties.py:18-20; feos.eos.{adash,bdash,kbdash}). */
+typedef struct sph_eos {
+    double adash, bdash, kbdash;
+} sph_eos;
+
+/* Caller-owned device buffers of one neighbour structure.  Sizes in elements. */
+typedef struct sph_buffers {
+    int32_t n;              /* particles */
+    int32_t max_nbrs;       /* ELL capacity per particle (multiple of 4) */
+    /* cell list */
+    uint32_t *cell_count;   /* [ncode]      */
+    uint32_t *cell_start;   /* [ncode + 1]  */
+    uint32_t *scan_tmp;     /* [sph_scan_tmp_elems(ncode)] */
+    uint32_t *code;         /* [n] cell code of particle i (original order) */
+    uint32_t *rank;         /* [n] arrival rank inside its cell */
+    int32_t *perm;          /* [n] sorted position -> original index */
+    /* Morton-sorted particle state */
+    double *pos4;           /* [n,4] x y z m              (32-byte aligned) */
+    double *vel4;           /* [n,4] vx vy vz press/rho^2 (32-byte aligned) */
+    float *rel4;            /* [n,4] fp32 position relative to the cell origin, cell code */
+    /* neighbour structure */
+    int32_t *nbr;           /* [ceil(n/32)*32 * max_nbrs] warp-transposed ELL rows */
+    int32_t *cnt;           /* [n] neighbours per sorted particle */
+    sph_status *status;     /* [1] */
+} sph_buffers;
+
+/* ------------------------------------------------------------------ host-side planning */
+
+/* Choose the cell grid for a periodic box (replaces nothing in the reference, which scans
+ * all n^2/2 pairs: neighbour_list.py:168-169).  occ_lo/occ_hi (may be NULL) are the extents
+ * the particles occupy; dimensions that are mostly empty get coarser cells so that the cell
+ * table stays O(n).  slab_lo/slab_layers (may be NULL) restrict the local grid to a range
+ * of global x cell layers for the multi-GPU slab decomposition. */
+int sph_grid_plan(const double box[3], double cutoff, double tolerance, int64_t n_hint,
+                  const double *occ_lo, const double *occ_hi, sph_grid *grid);
+int sph_grid_restrict_x(sph_grid *grid, int32_t first_layer, int32_t n_layers);
+
+/* Elements needed in sph_buffers.scan_tmp for a grid with `ncode` cell codes. */
+int64_t sph_scan_tmp_elems(uint32_t ncode);
+/* Elements needed in sph_buffers.nbr. */
+int64_t sph_nbr_elems(int32_t n, int32_t max_nbrs);
+
+/* ------------------------------------------------------------------ the hot path */
+
+int sph_status_reset(sph_status *d_status, void *stream);
+
+/* Cell list: counting-sort binning into Morton-ordered cells, deterministic order inside a
+ * cell (ascending original index).  Fills code, rank, cell_count, cell_start, perm.
+ * First half of VerletList.build (neighbour_list.py:160-189). */
+int sph_cells_build(const sph_grid *grid, const sph_buffers *buf, const double *d_r, void *stream);
+
+/* Reorder particle state into the Morton-sorted working set (pos4, vel4, rel4) using
+ * the existing perm.  Also what VerletList.separations amounts to when the list is kept
+ * and only positions moved (neighbour_list.py:236-252): it refreshes the operands from
+ * which every pair separation is recomputed on the fly. */
+int sph_gather(const sph_grid *grid, const sph_buffers *buf, const double *d_r, const double *d_v,
+               const double *d_m, void *stream);
+
+/* Neighbour structure: for every particle the set {j : rsq_ij < thr} under the reference's
+ * minimum image and predicate (neighbour_list.py:105-123,170-178), bit-exact, stored both
+ * ways (j in row i and i in row j).  Second half of VerletList.build. */
+int sph_nlist_build(const sph_grid *grid, const sph_buffers *buf, void *stream);
+
+/* Density summation + van der Waals EOS: properties.spam_properties (properties.py:63-120),
+ * f_properties.spam_properties (f_properties.py:16-147), c_properties.pyx:83-211.
+ * Reads t and writes rho, p, pco, u, t in ORIGINAL particle order (d_t is in/out, as p.t
+ * is in the reference) and leaves press/rho^2 in vel4[.,3] for sph_force.
+ * `use_hlr` != 0: long-range density only (rho_lr with h = hlr, no EOS;
+ * f_properties.py:102-107) -- d_p..d_t may then be NULL.
+ * `list_fresh` != 0 promises positions are those the cell list was built from. */
+int sph_density_eos(const sph_grid *grid, const sph_buffers *buf, const sph_eos *eos,
+                    const double *d_h_orig, int h_uniform, int list_fresh, int use_hlr,
+                    double *d_rho, double *d_p, double *d_pco, double *d_u, double *d_t,
+                    void *stream);
+
+/* Pair force and rates of change: forces.SpamForce.apply (forces.py:327-368),
+ * SpamForce2d (:246-274) with dim == 2, c_forces.SpamForce.apply (c_forces.pyx:62-115);
+ * with the cohesive pressure it is CohesiveSpamForce (forces.py:371-405,
+ * c_forces.pyx:131-182).  d_press and d_rho (original order) give press_i / rho_i^2; pass
+ * both NULL to reuse the values the preceding sph_density_eos left in vel4[.,3].
+ * ACCUMULATES into vdot[n,3], udot[n] (original order) as the reference does. */
+int sph_force(const sph_grid *grid, const sph_buffers *buf, const double *d_press,
+              const double *d_rho, const double *d_h_orig, int h_uniform, int list_fresh,
+              double fcutoff, int dim, double *d_vdot, double *d_udot, void *stream);
+
+/* ------------------------------------------------------------------ pair-list API surface */
+
+/* Lexicographic i<j pair list in ORIGINAL indices (what VerletList.build leaves in
+ * nl.iap, neighbour_list.py:186-189).  Two calls: count fills d_row_start[n+1] (exclusive
+ * scan of pairs per original i; d_row_start[n] = nip), fill writes iap[nip,2] (int32). */
+int sph_pairs_count(const sph_buffers *buf, uint32_t *d_row_count, void *stream);
+int sph_pairs_fill(const sph_buffers *buf, const uint32_t *d_row_start, int32_t *d_iap,
+                   int64_t cap_pairs, void *stream);
+/* Exclusive scan helper used between the two (also used by sph_cells_build). */
+int sph_exclusive_scan_u32(const uint32_t *d_in, uint32_t *d_out, uint32_t *d_tmp, int64_t n,
+                           void *stream);
+
+/* Per-pair separations for an explicit pair list: NeighbourList.separations
+ * (neighbour_list.py:63-83) / pairsep.pairsep (pairsep.pyx:25-81) + minimum image. */
+int sph_separations(const double box[3], const int32_t *d_iap, int64_t nip, const double *d_r,
+                    const double *d_v, double *d_drij, double *d_rij, double *d_rsq,
+                    double *d_dv, void *stream);
+
+/* Per-pair kernel values: spkernel.lucy_kernel (spkernel.py:86-118) with h of the first
+ * pair member (properties.py:88). */
+int sph_pair_kernels(const int32_t *d_iap, int64_t nip, const double *d_rij, const double *d_drij,
+                     const double *d_h, double *d_wij, double *d_dwij, void *stream);
+
+/* VerletList.compress (neighbour_list.py:191-223): drop listed neighbours that fail the
+ * predicate at the CURRENT sorted positions (after sph_gather). */
+int sph_compress(const sph_grid *grid, const sph_buffers *buf, void *stream);
+
+/* VerletList.ponder_rebuild (neighbour_list.py:225-234): status->rebuild = max|r_old-r|^2 > tol^2. */
+int sph_ponder_rebuild(const double *d_r_old, const double *d_r, int32_t n, double tol_sq,
+                       sph_status *d_status, void *stream);
+
+/* ------------------------------------------------------------------ stepping helpers ("next" rows) */
+
+/* x <- a + s * b over len doubles: the state-vector updates of integrator.py:37-41,44-59,62-95. */
+int sph_axpy(double *d_x, const double *d_a, const double *d_b, double s, int64_t len, void *stream);
+
+/* box.MirrorBox.apply (box.py:51-73) / box.PeriodicBox.apply (box.py:33-47). kind: 0 mirror, 1 periodic */
+int sph_box_apply(const double box[3], int kind, double *d_r, double *d_v, int32_t n, void *stream);
+
+const char *sph_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYTICLES_B200_H */

@@ -1,0 +1,218 @@
+"""Device-side neighbour structure: owns the torch buffers the C ABI works on.
+
+One NeighbourBackend = one cell grid + one Morton-sorted working set + one ELL neighbour
+structure (include/pyticles_b200.h: sph_grid, sph_buffers).  All memory is torch-owned; the
+CUDA library never allocates.  Nothing here computes on the CPU.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import SphBuffers, SphEos, SphGrid, SphStatus, box3, check
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f64(t, what):
+    if t.dtype != torch.float64 or not t.is_cuda or not t.is_contiguous():
+        raise _lib.SphError("%s must be a contiguous CUDA float64 tensor" % what)
+    return t
+
+
+class NeighbourBackend(object):
+    def __init__(self, device, max_nbrs=None):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.SphError("pyticles_b200 needs a CUDA device (got %s); there is no CPU path" % device)
+        self.grid = SphGrid()
+        self.grid_key = None
+        self.buf = SphBuffers()
+        self.n = 0
+        self.K = 0
+        self.user_max_nbrs = max_nbrs
+        self.t = {}
+        self.status_t = torch.zeros(16, dtype=torch.int32, device=self.device)
+        self.built = False
+        self.fresh = False          # sorted positions are the ones the list was built from
+        self.press_ready = False    # vel4[.,3] holds press/rho^2 of the last density pass
+
+    # ------------------------------------------------------------------ planning / memory
+    def plan(self, box, cutoff, tolerance, n, r=None, slab=None):
+        """Choose the cell grid.  Re-planned only when (box, cutoff, tolerance, n, slab) change;
+        the occupancy extents (one reduction + sync) only steer cell coarsening, never results."""
+        key = (tuple(float(b) for b in box), float(cutoff), float(tolerance), int(n), slab)
+        if key == self.grid_key:
+            return
+        lo = hi = None
+        if r is not None and n > 0:
+            ext = torch.stack([r[:n].amin(dim=0), r[:n].amax(dim=0)]).cpu()
+            if bool(torch.isfinite(ext).all()):
+                lo = box3(ext[0].tolist())
+                hi = box3(ext[1].tolist())
+        check(self.lib.sph_grid_plan(box3(box), float(cutoff), float(tolerance), int(n), lo, hi,
+                                     ctypes.byref(self.grid)), "sph_grid_plan")
+        if slab is not None:
+            check(self.lib.sph_grid_restrict_x(ctypes.byref(self.grid), int(slab[0]), int(slab[1])),
+                  "sph_grid_restrict_x")
+        self.grid_key = key
+        self.built = False
+
+    def expected_nbrs(self, n):
+        g = self.grid
+        vol = g.box[0] * g.box[1] * g.box[2]
+        rl = g.thr ** 0.5
+        return 4.18879 * rl ** 3 * (n / vol if vol > 0 else 0.0)
+
+    def _alloc(self, name, numel, dtype):
+        t = self.t.get(name)
+        if t is None or t.numel() < numel or t.dtype != dtype:
+            t = torch.empty(max(int(numel), 1), dtype=dtype, device=self.device)
+            self.t[name] = t
+        return t
+
+    def ensure(self, n, K=None):
+        g = self.grid
+        if K is None:
+            K = self.user_max_nbrs
+        if K is None:
+            K = self.K if (self.K and n == self.n) else int(1.6 * self.expected_nbrs(n)) + 24
+        K = max(8, min(int(K), max(n - 1, 8)))
+        K = (K + 3) // 4 * 4
+        self.n, self.K = int(n), K
+        ncode = int(g.ncode)
+        b = self.buf
+        b.n, b.max_nbrs = self.n, self.K
+        b.cell_count = _ptr(self._alloc("cell_count", ncode, torch.int32))
+        b.cell_start = _ptr(self._alloc("cell_start", ncode + 1, torch.int32))
+        b.scan_tmp = _ptr(self._alloc("scan_tmp", self.lib.sph_scan_tmp_elems(ncode), torch.int32))
+        b.code = _ptr(self._alloc("code", n, torch.int32))
+        b.rank = _ptr(self._alloc("rank", n, torch.int32))
+        b.perm = _ptr(self._alloc("perm", n, torch.int32))
+        b.pos4 = _ptr(self._alloc("pos4", 4 * n, torch.float64))
+        b.vel4 = _ptr(self._alloc("vel4", 4 * n, torch.float64))
+        b.rel4 = _ptr(self._alloc("rel4", 4 * n, torch.float32))
+        b.nbr = _ptr(self._alloc("nbr", self.lib.sph_nbr_elems(n, self.K), torch.int32))
+        b.cnt = _ptr(self._alloc("cnt", n, torch.int32))
+        b.status = _ptr(self.status_t)
+
+    # ------------------------------------------------------------------ the hot path
+    def cells_and_list(self, r, v, m, check_overflow=True):
+        """sph_status_reset + sph_cells_build + sph_gather + sph_nlist_build on the current stream."""
+        L, g, b, s = self.lib, ctypes.byref(self.grid), ctypes.byref(self.buf), _stream()
+        _f64(r, "r"), _f64(v, "v"), _f64(m, "m")
+        check(L.sph_status_reset(_ptr(self.status_t), s), "sph_status_reset")
+        check(L.sph_cells_build(g, b, _ptr(r), s), "sph_cells_build")
+        check(L.sph_gather(g, b, _ptr(r), _ptr(v), _ptr(m), s), "sph_gather")
+        check(L.sph_nlist_build(g, b, s), "sph_nlist_build")
+        self.built = True
+        self.fresh = True
+        self.press_ready = False
+        if check_overflow:
+            self.resolve_overflow()
+
+    def resolve_overflow(self):
+        """Read the status block (one small D2H copy); grow the ELL capacity and redo the
+        neighbour pass if some particle had more neighbours than max_nbrs."""
+        st = self.status()
+        while st.flags & _lib.SPH_F_NBR_OVERFLOW:
+            need = int(st.max_count)
+            self.user_max_nbrs = None
+            self.ensure(self.n, K=need + max(4, need // 8))
+            L, s = self.lib, _stream()
+            self.status_t[0] &= ~_lib.SPH_F_NBR_OVERFLOW
+            check(L.sph_nlist_build(ctypes.byref(self.grid), ctypes.byref(self.buf), s), "sph_nlist_build")
+            st = self.status()
+        return st
+
+    def regather(self, r, v, m, moved):
+        check(self.lib.sph_gather(ctypes.byref(self.grid), ctypes.byref(self.buf), _ptr(_f64(r, "r")),
+                                  _ptr(_f64(v, "v")), _ptr(_f64(m, "m")), _stream()), "sph_gather")
+        if moved:
+            self.fresh = False
+        self.press_ready = False
+
+    def density_eos(self, eos, h, h_uniform, rho, p, pco, u, t, long_range=False):
+        e = SphEos(float(eos[0]), float(eos[1]), float(eos[2]))
+        check(self.lib.sph_density_eos(ctypes.byref(self.grid), ctypes.byref(self.buf), ctypes.byref(e),
+                                       _ptr(_f64(h, "h")), int(bool(h_uniform)), int(self.fresh),
+                                       int(bool(long_range)), _ptr(rho), _ptr(p), _ptr(pco), _ptr(u), _ptr(t),
+                                       _stream()), "sph_density_eos")
+        self.press_ready = not long_range
+
+    def force(self, press, rho, h, h_uniform, fcutoff, dim, vdot, udot, reuse_press=False):
+        if reuse_press and self.press_ready:
+            pp = rp = ctypes.c_void_p(0)
+        else:
+            pp, rp = _ptr(_f64(press, "press")), _ptr(_f64(rho, "rho"))
+            self.press_ready = False
+        check(self.lib.sph_force(ctypes.byref(self.grid), ctypes.byref(self.buf), pp, rp, _ptr(_f64(h, "h")),
+                                 int(bool(h_uniform)), int(self.fresh), float(fcutoff), int(dim),
+                                 _ptr(_f64(vdot, "vdot")), _ptr(_f64(udot, "udot")), _stream()), "sph_force")
+
+    def compress(self):
+        check(self.lib.sph_compress(ctypes.byref(self.grid), ctypes.byref(self.buf), _stream()), "sph_compress")
+
+    # ------------------------------------------------------------------ host-visible results
+    def status(self):
+        raw = self.status_t.cpu().numpy().tobytes()
+        return SphStatus.from_buffer_copy(raw)
+
+    def ponder_rebuild(self, r_old, r, n, tol_sq):
+        check(self.lib.sph_ponder_rebuild(_ptr(r_old), _ptr(r), int(n), float(tol_sq), _ptr(self.status_t),
+                                          _stream()), "sph_ponder_rebuild")
+        return bool(self.status().rebuild)
+
+    def export_pairs(self):
+        """Lexicographic i<j pair list in original indices: int32 tensor [nip, 2]."""
+        n = self.n
+        L, b, s = self.lib, ctypes.byref(self.buf), _stream()
+        if n == 0:
+            return torch.zeros((0, 2), dtype=torch.int32, device=self.device)
+        row_count = torch.empty(n, dtype=torch.int32, device=self.device)
+        row_start = torch.empty(n + 1, dtype=torch.int32, device=self.device)
+        tmp = torch.empty(int(L.sph_scan_tmp_elems(n)), dtype=torch.int32, device=self.device)
+        check(L.sph_pairs_count(b, _ptr(row_count), s), "sph_pairs_count")
+        check(L.sph_exclusive_scan_u32(_ptr(row_count), _ptr(row_start), _ptr(tmp), n, s), "sph_exclusive_scan_u32")
+        nip = int(row_start[n].item()) & 0xFFFFFFFF
+        iap = torch.empty((nip, 2), dtype=torch.int32, device=self.device)
+        check(L.sph_pairs_fill(b, _ptr(row_start), _ptr(iap), nip, s), "sph_pairs_fill")
+        return iap
+
+    def count_links(self):
+        return int(self.t["cnt"][:self.n].clamp(max=self.K).sum(dtype=torch.int64).item())
+
+    def separations(self, box, iap, r, v):
+        nip = iap.shape[0]
+        dev = self.device
+        drij = torch.empty((nip, 3), dtype=torch.float64, device=dev)
+        dv = torch.empty((nip, 3), dtype=torch.float64, device=dev)
+        rij = torch.empty(nip, dtype=torch.float64, device=dev)
+        rsq = torch.empty(nip, dtype=torch.float64, device=dev)
+        check(self.lib.sph_separations(box3(box), _ptr(iap), nip, _ptr(r), _ptr(v), _ptr(drij), _ptr(rij),
+                                       _ptr(rsq), _ptr(dv), _stream()), "sph_separations")
+        return drij, rij, rsq, dv
+
+    def pair_kernels(self, iap, rij, drij, h):
+        nip = iap.shape[0]
+        wij = torch.empty(nip, dtype=torch.float64, device=self.device)
+        dwij = torch.empty((nip, 3), dtype=torch.float64, device=self.device)
+        check(self.lib.sph_pair_kernels(_ptr(iap), nip, _ptr(rij), _ptr(drij), _ptr(_f64(h, "h")), _ptr(wij),
+                                        _ptr(dwij), _stream()), "sph_pair_kernels")
+        return wij, dwij
+
+
+def axpy(x, a, b, s):
+    """x <- a + s*b (integrator.py:40,53,57) on the current stream."""
+    check(_lib.load().sph_axpy(_ptr(x), _ptr(a), _ptr(b), float(s), x.numel(), _stream()), "sph_axpy")
+
+
+def box_apply(box, kind, r, v, n):
+    check(_lib.load().sph_box_apply(box3(box), int(kind), _ptr(r), _ptr(v), int(n), _stream()), "sph_box_apply")

@@ -1,0 +1,1136 @@
+// pyticles_b200 -- hand-written sm_100a kernels of the SPH step hot path + their C ABI.
+//
+// Design in one paragraph (DESIGN.md has the long form).  Particles are binned into a
+// periodic cell grid (cell width >= list radius), cells are numbered along a generalised
+// Morton curve, and a counting sort gives a Morton-ordered permutation.  The particle
+// state is gathered once per evaluation into packed, 32-byte rows in that order
+// (pos4 = x y z m, vel4 = vx vy vz press/rho^2, rel4 = fp32 cell-relative position).  The
+// neighbour pass runs one warp per cell: candidates from the 27 surrounding cells are
+// staged in shared memory, every lane tests one candidate against the cell's particles in
+// fp32 with a rigorous error band, the rare in-band candidates are decided by the
+// reference's own fp64 predicate, and accepted neighbours are compacted with warp ballots
+// into warp-transposed ELL rows.  Density/EOS and force passes run one thread per
+// particle over those rows with fp64 accumulation in registers: no atomics, fixed
+// summation order, bit-reproducible results.
+//
+// Reference semantics restated here (file:line into the reference tree):
+//   minimum image      neighbour_list.py:105-123
+//   pair predicate     neighbour_list.py:170-178   rsq < cutoff^2 + tolerance^2, strict
+//   Lucy kernel        spkernel.py:86-118
+//   density, EOS       properties.py:38-49,63-120
+//   pressure force     forces.py:38-42,327-368 (2-D :246-274; cohesive :371-405)
+//   list maintenance   neighbour_list.py:191-234
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "pyticles_b200.h"
+
+#define SPH_PI 3.14159265358979323846
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kNlWarps = 8;          // warps per block in the neighbour pass
+constexpr int kNlWin = 512;          // candidates staged per warp per window
+
+struct __align__(16) d2 { double x, y; };
+
+__device__ __forceinline__ void load4(const double *p, double &a, double &b, double &c, double &d)
+{
+    const double2 u = __ldg(reinterpret_cast<const double2 *>(p));
+    const double2 w = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    a = u.x; b = u.y; c = w.x; d = w.y;
+}
+
+__device__ __forceinline__ uint32_t pdep32(uint32_t v, uint32_t mask)
+{
+    uint32_t r = 0;
+    while (mask) {
+        const uint32_t low = mask & (0u - mask);
+        if (v & 1u) r |= low;
+        v >>= 1;
+        mask ^= low;
+    }
+    return r;
+}
+
+__device__ __forceinline__ uint32_t pext32(uint32_t v, uint32_t mask)
+{
+    uint32_t r = 0, bit = 1;
+    while (mask) {
+        const uint32_t low = mask & (0u - mask);
+        if (v & low) r |= bit;
+        bit <<= 1;
+        mask ^= low;
+    }
+    return r;
+}
+
+// neighbour_list.py:111-122 -- one shift, strict comparisons against L/2.
+__device__ __forceinline__ double min_image(double d, double L, double half)
+{
+    if (d > half) d = __dsub_rn(d, L);
+    if (d < -half) d = __dadd_rn(d, L);
+    return d;
+}
+
+// rsq exactly as numpy forms it: (dx*dx + dy*dy) + dz*dz, every operation rounded.
+__device__ __forceinline__ double rsq_exact(double dx, double dy, double dz)
+{
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// The reference's pair predicate on the reference's operands (neighbour_list.py:170-178).
+__device__ __forceinline__ bool pair_exact(const sph_grid &g, const double *pos4, int a, int j)
+{
+    double ax, ay, az, am, bx, by, bz, bm;
+    load4(pos4 + 4 * (size_t)a, ax, ay, az, am);
+    load4(pos4 + 4 * (size_t)j, bx, by, bz, bm);
+    const double dx = min_image(__dsub_rn(bx, ax), g.box[0], g.box[0] / 2.);
+    const double dy = min_image(__dsub_rn(by, ay), g.box[1], g.box[1] / 2.);
+    const double dz = min_image(__dsub_rn(bz, az), g.box[2], g.box[2] / 2.);
+    return rsq_exact(dx, dy, dz) < g.thr;
+}
+
+// ------------------------------------------------------------------ binning
+struct CellLoc {
+    uint32_t code;
+    float rx, ry, rz;
+    uint32_t flags;
+};
+
+__device__ __forceinline__ int cell_coord(const sph_grid &g, int d, double x, float &rel, uint32_t &flags)
+{
+    const double L = g.box[d];
+    if (!(x >= 0.0 && x < L)) {
+        flags |= SPH_F_OUT_OF_BOX;
+        if (!(x >= -0.25 * L && x <= 1.25 * L)) flags |= SPH_F_OUT_OF_RANGE;
+        if (!(fabs(x) <= 1.0e300)) flags |= SPH_F_NONFINITE;
+    }
+    double f = floor(x * g.inv_w[d]);
+    if (!(fabs(f) < 4.0e15)) f = 0.0;                 // NaN / absurd: any cell, exact path decides
+    const long long cu = (long long)f;
+    rel = (float)(x - (double)cu * g.w[d]);
+    long long cg = cu % g.nc[d];
+    if (cg < 0) cg += g.nc[d];
+    int cl = (int)cg - g.lo[d];
+    if (cl < 0) cl += g.nc[d];
+    if (cl >= g.ncl[d]) { flags |= SPH_F_OUT_OF_SLAB; cl = g.ncl[d] - 1; }
+    return cl;
+}
+
+__device__ __forceinline__ CellLoc locate(const sph_grid &g, double x, double y, double z)
+{
+    CellLoc c;
+    c.flags = 0;
+    const int cx = cell_coord(g, 0, x, c.rx, c.flags);
+    const int cy = cell_coord(g, 1, y, c.ry, c.flags);
+    const int cz = cell_coord(g, 2, z, c.rz, c.flags);
+    c.code = pdep32((uint32_t)cx, g.mask[0]) | pdep32((uint32_t)cy, g.mask[1]) |
+             pdep32((uint32_t)cz, g.mask[2]);
+    return c;
+}
+
+__global__ void __launch_bounds__(kBlock)
+bin_kernel(const __grid_constant__ sph_grid g, const double *__restrict__ r, int n,
+           uint32_t *__restrict__ cell_count, uint32_t *__restrict__ code,
+           uint32_t *__restrict__ rank, sph_status *__restrict__ status)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t flags = 0;
+    if (i < n) {
+        const CellLoc c = locate(g, r[3 * (size_t)i], r[3 * (size_t)i + 1], r[3 * (size_t)i + 2]);
+        flags = c.flags;
+        code[i] = c.code;
+        rank[i] = atomicAdd(cell_count + c.code, 1u);
+    }
+    flags = __reduce_or_sync(0xffffffffu, flags);
+    if (flags && (threadIdx.x & 31) == 0) atomicOr(&status->flags, flags);
+}
+
+__global__ void __launch_bounds__(kBlock)
+scatter_kernel(int n, const uint32_t *__restrict__ code, const uint32_t *__restrict__ rank,
+               const uint32_t *__restrict__ cell_start, int32_t *__restrict__ perm)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[cell_start[code[i]] + rank[i]] = i;
+}
+
+// Arrival order inside a cell comes from atomics; make it canonical (ascending original
+// index) so that every later sum runs in a fixed order.
+__global__ void __launch_bounds__(kBlock)
+cell_sort_kernel(uint32_t ncode, const uint32_t *__restrict__ cell_start, int32_t *__restrict__ perm)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncode) return;
+    const uint32_t s = cell_start[c], e = cell_start[c + 1];
+    for (uint32_t k = s + 1; k < e; ++k) {
+        const int32_t v = perm[k];
+        uint32_t q = k;
+        while (q > s && perm[q - 1] > v) { perm[q] = perm[q - 1]; --q; }
+        perm[q] = v;
+    }
+}
+
+// ------------------------------------------------------------------ exclusive scan (uint32)
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kBlock * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t &total)
+{
+    __shared__ uint32_t warp_sums[kBlock / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = lane < kBlock / 32 ? warp_sums[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < kBlock / 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane < kBlock / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    total = warp_sums[kBlock / 32 - 1];
+    const uint32_t base = wid ? warp_sums[wid - 1] : 0u;
+    __syncthreads();
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(kBlock)
+scan_tile_sums(const uint32_t *__restrict__ in, int64_t n, uint32_t *__restrict__ tile_sum)
+{
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        const int64_t i = base + (int64_t)k * kBlock + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    uint32_t total;
+    block_exclusive_scan(s, total);
+    if (threadIdx.x == 0) tile_sum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kBlock)
+scan_tile_offsets(uint32_t *__restrict__ tile_sum, int64_t ntiles)
+{
+    uint32_t carry = 0;
+    for (int64_t base = 0; base < ntiles; base += kBlock) {
+        const int64_t i = base + threadIdx.x;
+        const uint32_t v = i < ntiles ? tile_sum[i] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_exclusive_scan(v, total);
+        if (i < ntiles) tile_sum[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) tile_sum[ntiles] = carry;
+}
+
+__global__ void __launch_bounds__(kBlock)
+scan_tile_apply(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, int64_t n,
+                const uint32_t *__restrict__ tile_off, int64_t ntiles)
+{
+    // thread t owns kScanItems consecutive elements of the tile
+    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (base + k < n) ? in[base + k] : 0u;
+        s += v[k];
+    }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(s, total) + tile_off[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        if (base + k < n) out[base + k] = ex;
+        ex += v[k];
+    }
+    if (blockIdx.x == ntiles - 1 && threadIdx.x == 0) out[n] = tile_off[ntiles];
+}
+
+// ------------------------------------------------------------------ gather into Morton order
+__global__ void __launch_bounds__(kBlock)
+gather_kernel(const __grid_constant__ sph_grid g, int n, const int32_t *__restrict__ perm,
+              const double *__restrict__ r, const double *__restrict__ v,
+              const double *__restrict__ m, double *__restrict__ pos4, double *__restrict__ vel4,
+              float *__restrict__ rel4)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const size_t i = (size_t)perm[a];
+    const double x = r[3 * i], y = r[3 * i + 1], z = r[3 * i + 2];
+    const CellLoc c = locate(g, x, y, z);
+    double2 *p = reinterpret_cast<double2 *>(pos4 + 4 * (size_t)a);
+    p[0] = make_double2(x, y);
+    p[1] = make_double2(z, m[i]);
+    double2 *q = reinterpret_cast<double2 *>(vel4 + 4 * (size_t)a);
+    q[0] = make_double2(v[3 * i], v[3 * i + 1]);
+    q[1] = make_double2(v[3 * i + 2], 0.0);
+    reinterpret_cast<float4 *>(rel4)[a] = make_float4(c.rx, c.ry, c.rz, __uint_as_float(c.code));
+}
+
+// ------------------------------------------------------------------ neighbour pass
+__device__ __forceinline__ float wrap32(float d, float L)
+{
+    const float half = 0.5f * L;
+    if (d > half) d -= L;
+    if (d < -half) d += L;
+    return d;
+}
+
+__global__ void __launch_bounds__(kNlWarps * 32)
+nlist_kernel(const __grid_constant__ sph_grid g, int n, int K,
+             const uint32_t *__restrict__ cell_start, const float *__restrict__ rel4,
+             const double *__restrict__ pos4, int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
+             sph_status *__restrict__ status)
+{
+    extern __shared__ float4 smem_cand[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    float4 *S = smem_cand + wib * kNlWin;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const bool fast = !(status->flags & (SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
+    const float4 *rel = reinterpret_cast<const float4 *>(rel4);
+    const bool small_x = g.ncl[0] < 3, small_y = g.ncl[1] < 3, small_z = g.ncl[2] < 3;
+    const float Lx = (float)g.box[0], Ly = (float)g.box[1], Lz = (float)g.box[2];
+    uint32_t local_max = 0;
+
+    const uint32_t nwarps = gridDim.x * kNlWarps;
+    for (uint32_t c = blockIdx.x * kNlWarps + wib; c < g.ncode; c += nwarps) {
+        const uint32_t cs = cell_start[c], ce = cell_start[c + 1];
+        if (cs == ce) continue;
+        const int cx = (int)pext32(c, g.mask[0]), cy = (int)pext32(c, g.mask[1]),
+                  cz = (int)pext32(c, g.mask[2]);
+        // lane q < 27 owns neighbour cell q
+        uint32_t nstart = 0, ncount = 0;
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        if (lane < 27) {
+            int o[3] = {lane % 3 - 1, (lane / 3) % 3 - 1, lane / 9 - 1};
+            const int cc[3] = {cx, cy, cz};
+            int nb[3];
+            bool ok = true;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (g.ncl[d] >= 3) {
+                    int t = cc[d] + o[d];
+                    if (t < 0 || t >= g.ncl[d]) {
+                        if (g.wrap[d]) t += (t < 0) ? g.ncl[d] : -g.ncl[d];
+                        else ok = false;
+                    }
+                    nb[d] = t;
+                } else {                          // 1 or 2 layers: visit each layer once
+                    const int t = o[d] + 1;
+                    if (t >= g.ncl[d]) ok = false;
+                    nb[d] = t;
+                    o[d] = t - cc[d];
+                }
+            }
+            if (ok) {
+                const uint32_t code = pdep32((uint32_t)nb[0], g.mask[0]) |
+                                      pdep32((uint32_t)nb[1], g.mask[1]) |
+                                      pdep32((uint32_t)nb[2], g.mask[2]);
+                nstart = cell_start[code];
+                ncount = cell_start[code + 1] - nstart;
+                fx = (float)((double)o[0] * g.w[0]);
+                fy = (float)((double)o[1] * g.w[1]);
+                fz = (float)((double)o[2] * g.w[2]);
+            }
+        }
+        uint32_t incl = ncount;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t prefix = incl - ncount;
+
+        for (uint32_t wbase = 0; wbase < total; wbase += kNlWin) {
+            __syncwarp();
+            for (int q = 0; q < 27; ++q) {
+                const uint32_t ct = __shfl_sync(0xffffffffu, ncount, q);
+                const uint32_t pf = __shfl_sync(0xffffffffu, prefix, q);
+                const uint32_t st = __shfl_sync(0xffffffffu, nstart, q);
+                const float sx = __shfl_sync(0xffffffffu, fx, q);
+                const float sy = __shfl_sync(0xffffffffu, fy, q);
+                const float sz = __shfl_sync(0xffffffffu, fz, q);
+                if (ct == 0 || pf + ct <= wbase || pf >= wbase + kNlWin) continue;
+                for (uint32_t t = lane; t < ct; t += 32) {
+                    const uint32_t s = pf + t;
+                    if (s >= wbase && s < wbase + kNlWin) {
+                        const float4 p = __ldg(rel + st + t);
+                        S[s - wbase] = make_float4(p.x + sx, p.y + sy, p.z + sz,
+                                                   __int_as_float((int)(st + t)));
+                    }
+                }
+            }
+            __syncwarp();
+            const uint32_t nS = min((uint32_t)kNlWin, total - wbase);
+            for (uint32_t a = cs; a < ce; ++a) {
+                const float4 pi = __ldg(rel + a);
+                uint32_t cnt_i = wbase ? (uint32_t)cnt[a] : 0u;
+                int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
+                for (uint32_t s0 = 0; s0 < nS; s0 += 32) {
+                    const uint32_t s = s0 + lane;
+                    const bool valid = s < nS;
+                    const float4 cd = S[valid ? s : 0];
+                    float dx = cd.x - pi.x, dy = cd.y - pi.y, dz = cd.z - pi.z;
+                    if (small_x) dx = wrap32(dx, Lx);
+                    if (small_y) dy = wrap32(dy, Ly);
+                    if (small_z) dz = wrap32(dz, Lz);
+                    const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    const int j = __float_as_int(cd.w);
+                    const bool other = valid && (uint32_t)j != a;
+                    bool inside = other && fast && rsq < g.thr_in;
+                    const bool border = other && !inside && (!fast || rsq < g.thr_out);
+                    if (__any_sync(0xffffffffu, border)) {
+                        if (border) inside = pair_exact(g, pos4, (int)a, j);
+                    }
+                    const uint32_t mask = __ballot_sync(0xffffffffu, inside);
+                    if (inside) {
+                        const uint32_t pos = cnt_i + __popc(mask & lt_mask);
+                        if (pos < (uint32_t)K) row[(size_t)pos * 32] = j;
+                    }
+                    cnt_i += __popc(mask);
+                }
+                if (lane == 0) cnt[a] = (int32_t)cnt_i;
+                local_max = max(local_max, cnt_i);
+            }
+        }
+    }
+    if (lane == 0 && local_max > 0) {
+        if (local_max > *(volatile uint32_t *)&status->max_count) atomicMax(&status->max_count, local_max);
+        if (local_max > (uint32_t)K) atomicOr(&status->flags, SPH_F_NBR_OVERFLOW);
+    }
+}
+
+// particles that sit in no cell the neighbour pass visited cannot exist (every particle is
+// in a cell), but rows of EMPTY trailing lanes must read as zero neighbours.
+// ------------------------------------------------------------------ per-particle passes
+struct Interior {
+    bool skip;   // warp-uniform: no pair of this warp can need the minimum-image shift
+};
+
+__device__ __forceinline__ bool cell_is_interior(const sph_grid &g, uint32_t code)
+{
+    bool in = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        int cg = (int)pext32(code, g.mask[d]) + g.lo[d];
+        if (cg >= g.nc[d]) cg -= g.nc[d];
+        in = in && g.nc[d] >= 5 && cg >= 1 && cg <= g.nc[d] - 2;
+    }
+    return in;
+}
+
+__device__ __forceinline__ double lucy_norm3(double h)
+{
+    return 105. / (SPH_PI * 16. * (h * h * h));       // spkernel.py:99
+}
+
+template <bool UNIFORM_H, bool WRAP>
+__device__ __forceinline__ double density_row(const sph_grid &g, const double *__restrict__ pos4,
+                                              const int32_t *__restrict__ perm,
+                                              const double *__restrict__ h_orig,
+                                              const int32_t *__restrict__ row, int count, int orig,
+                                              double ax, double ay, double az, double hinv, double qn)
+{
+    double acc = 0.0;
+    const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
+    for (int k = 0; k < count; ++k) {
+        const int j = row[(size_t)k * 32];
+        double bx, by, bz, bm;
+        load4(pos4 + 4 * (size_t)j, bx, by, bz, bm);
+        double dx = bx - ax, dy = by - ay, dz = bz - az;
+        if (WRAP) {
+            dx = min_image(dx, g.box[0], hx);
+            dy = min_image(dy, g.box[1], hy);
+            dz = min_image(dz, g.box[2], hz);
+        }
+        const double rsq = rsq_exact(dx, dy, dz);
+        const double rr = sqrt(rsq);
+        double hi = hinv, q = qn;
+        if (!UNIFORM_H) {
+            const int oj = perm[j];
+            const double h = h_orig[oj < orig ? oj : orig];       // properties.py:88: h of the first member
+            hi = 1.0 / h;
+            q = lucy_norm3(h);
+        }
+        const double s = rr * hi;
+        if (s < 1.0) {                                            // spkernel.py:106
+            const double t = 1.0 - s;
+            acc += (q * (1.0 + 3.0 * s) * (t * t * t)) * bm;      // spkernel.py:107, properties.py:90-91
+        }
+    }
+    return acc;
+}
+
+template <bool UNIFORM_H>
+__global__ void __launch_bounds__(kBlock)
+density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__restrict__ pos4,
+               double *__restrict__ vel4, const float *__restrict__ rel4,
+               const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
+               const int32_t *__restrict__ cnt, const sph_status *__restrict__ status,
+               const double *__restrict__ h_orig, sph_eos eos, int list_fresh, int long_range,
+               double *__restrict__ rho_out, double *__restrict__ p_out, double *__restrict__ pco_out,
+               double *__restrict__ u_out, double *__restrict__ t_io)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = a < n;
+    double ax = 0, ay = 0, az = 0, am = 0;
+    int count = 0, orig = 0;
+    bool interior = true;
+    if (active) {
+        load4(pos4 + 4 * (size_t)a, ax, ay, az, am);
+        count = min(cnt[a], K);
+        orig = perm[a];
+        interior = cell_is_interior(g, __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w));
+    }
+    const bool can_skip = list_fresh && !(status->flags & (SPH_F_OUT_OF_BOX | SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
+    const bool skip = __all_sync(0xffffffffu, interior) && can_skip;
+    const double h0 = h_orig[0];
+    const double hinv = 1.0 / h0, qn = lucy_norm3(h0);
+    const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
+    double sum;
+    if (skip) sum = density_row<UNIFORM_H, false>(g, pos4, perm, h_orig, row, count, orig, ax, ay, az, hinv, qn);
+    else sum = density_row<UNIFORM_H, true>(g, pos4, perm, h_orig, row, count, orig, ax, ay, az, hinv, qn);
+    if (!active) return;
+    // properties.py:76-77: every particle starts from W(0; h[0]) -- not m_i * W(0; h_i)
+    const double rho = qn + sum;
+    rho_out[orig] = rho;
+    if (long_range) return;
+    const double t = t_io[orig];
+    const double p = (rho * eos.kbdash * t) / (1 - rho * eos.bdash);        // properties.py:41
+    const double pco = -eos.adash * rho * rho;
+    const double u = t * eos.kbdash - eos.adash * rho;                      // properties.py:46,119
+    p_out[orig] = p;
+    pco_out[orig] = pco;
+    u_out[orig] = u;
+    t_io[orig] = (u + eos.adash * rho) / eos.kbdash;                        // properties.py:49,120
+    vel4[4 * (size_t)a + 3] = p / (rho * rho);                              // forces.py:353 operand
+}
+
+__global__ void __launch_bounds__(kBlock)
+pressure_term_kernel(int n, const int32_t *__restrict__ perm, const double *__restrict__ press,
+                     const double *__restrict__ rho, double *__restrict__ vel4)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const int o = perm[a];
+    const double d = rho[o];
+    vel4[4 * (size_t)a + 3] = press[o] / (d * d);
+}
+
+struct ForceAcc { double ax, ay, az, du; };
+
+template <bool UNIFORM_H, bool WRAP>
+__device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *__restrict__ pos4,
+                                              const double *__restrict__ vel4,
+                                              const int32_t *__restrict__ perm,
+                                              const double *__restrict__ h_orig,
+                                              const int32_t *__restrict__ row, int count, int orig,
+                                              double px, double py, double pz, double vx, double vy,
+                                              double vz, double Ai, double hinv, double c2,
+                                              double fcutsq, bool two_d)
+{
+    ForceAcc f = {0.0, 0.0, 0.0, 0.0};
+    const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
+    for (int k = 0; k < count; ++k) {
+        const int j = row[(size_t)k * 32];
+        double bx, by, bz, bm, wx, wy, wz, Aj;
+        load4(pos4 + 4 * (size_t)j, bx, by, bz, bm);
+        load4(vel4 + 4 * (size_t)j, wx, wy, wz, Aj);
+        // Pair (i<j in original order) contributes +a to i and -a to j with dr = r_j - r_i.
+        // Seen from this particle: dr = r_other - r_self and the term enters with +.
+        double dx = bx - px, dy = by - py, dz = bz - pz;
+        if (WRAP) {
+            dx = min_image(dx, g.box[0], hx);
+            dy = min_image(dy, g.box[1], hy);
+            dz = min_image(dz, g.box[2], hz);
+        }
+        const double rsq = rsq_exact(dx, dy, dz);
+        const double rr = sqrt(rsq);
+        double hi = hinv, cc = c2;
+        if (!UNIFORM_H) {
+            const int oj = perm[j];
+            const double h = h_orig[oj < orig ? oj : orig];
+            hi = 1.0 / h;
+            cc = -12.0 * lucy_norm3(h) * hi * hi;
+        }
+        const double s = rr * hi;
+        // forces.py:40 cutoff on rij^2; spkernel.py:106,109: zero outside h and at r == 0
+        if (s < 1.0 && rr * rr <= fcutsq) {
+            // q(-12 r^3/h^4 + 24 r^2/h^3 - 12 r/h^2)/r = -(12 q / h^2) (1 - r/h)^2   (spkernel.py:113-114)
+            const double t = 1.0 - s;
+            const double fac = (cc * (t * t)) * (Ai + Aj);          // ps * dW/dr / r  (forces.py:353-357)
+            const double gx = fac * dx, gy = fac * dy, gz = two_d ? 0.0 : fac * dz;
+            f.ax += gx;
+            f.ay += gy;
+            f.az += gz;
+            // du = 0.5 * a . dv with dv = v_j - v_i; symmetric in the pair (forces.py:366-368)
+            const double dot = gx * (wx - vx) + gy * (wy - vy) + gz * (wz - vz);
+            f.du += (0.5 * dot) * bm;
+        }
+    }
+    return f;
+}
+
+template <bool UNIFORM_H>
+__global__ void __launch_bounds__(kBlock)
+force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__restrict__ pos4,
+             const double *__restrict__ vel4, const float *__restrict__ rel4,
+             const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
+             const int32_t *__restrict__ cnt, const sph_status *__restrict__ status,
+             const double *__restrict__ h_orig, int list_fresh, double fcutsq, int dim,
+             double *__restrict__ vdot, double *__restrict__ udot)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = a < n;
+    double px = 0, py = 0, pz = 0, pm = 0, vx = 0, vy = 0, vz = 0, Ai = 0;
+    int count = 0, orig = 0;
+    bool interior = true;
+    if (active) {
+        load4(pos4 + 4 * (size_t)a, px, py, pz, pm);
+        load4(vel4 + 4 * (size_t)a, vx, vy, vz, Ai);
+        count = min(cnt[a], K);
+        orig = perm[a];
+        interior = cell_is_interior(g, __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w));
+    }
+    const bool can_skip = list_fresh && !(status->flags & (SPH_F_OUT_OF_BOX | SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
+    const bool skip = __all_sync(0xffffffffu, interior) && can_skip;
+    const double h0 = h_orig[0];
+    const double hinv = 1.0 / h0, c2 = -12.0 * lucy_norm3(h0) * hinv * hinv;
+    const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
+    ForceAcc f;
+    if (skip) f = force_row<UNIFORM_H, false>(g, pos4, vel4, perm, h_orig, row, count, orig, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
+    else f = force_row<UNIFORM_H, true>(g, pos4, vel4, perm, h_orig, row, count, orig, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
+    if (!active) return;
+    (void)pm;
+    // the reference accumulates into vdot/udot (particles.py:549-550 zeroes them per evaluation)
+    vdot[3 * (size_t)orig] += f.ax;
+    vdot[3 * (size_t)orig + 1] += f.ay;
+    vdot[3 * (size_t)orig + 2] += f.az;
+    udot[orig] += f.du;
+}
+
+// ------------------------------------------------------------------ list maintenance / export
+__global__ void __launch_bounds__(kBlock)
+compress_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__restrict__ pos4,
+                int32_t *__restrict__ nbr, int32_t *__restrict__ cnt)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
+    const int count = min(cnt[a], K);
+    int q = 0;
+    for (int k = 0; k < count; ++k) {
+        const int j = row[(size_t)k * 32];
+        if (pair_exact(g, pos4, a, j)) row[(size_t)(q++) * 32] = j;
+    }
+    cnt[a] = q;
+}
+
+__global__ void __launch_bounds__(kBlock)
+pairs_count_kernel(int n, int K, const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
+                   const int32_t *__restrict__ cnt, uint32_t *__restrict__ row_count)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
+    const int count = min(cnt[a], K);
+    const int oi = perm[a];
+    uint32_t c = 0;
+    for (int k = 0; k < count; ++k) c += perm[row[(size_t)k * 32]] > oi;
+    row_count[oi] = c;
+}
+
+constexpr int kExportMax = 256;   // neighbours sorted in local memory per particle
+
+__global__ void __launch_bounds__(128)
+pairs_fill_kernel(int n, int K, const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
+                  const int32_t *__restrict__ cnt, const uint32_t *__restrict__ row_start,
+                  int32_t *__restrict__ iap, int64_t cap)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
+    const int count = min(cnt[a], K);
+    const int oi = perm[a];
+    int32_t js[kExportMax];
+    int m = 0;
+    int64_t base = row_start[oi];
+    // rows longer than kExportMax are emitted in sorted chunks by repeated selection
+    int last = oi;
+    for (;;) {
+        m = 0;
+        for (int k = 0; k < count; ++k) {
+            const int oj = perm[row[(size_t)k * 32]];
+            if (oj <= last) continue;
+            // keep the kExportMax smallest candidates above `last`, sorted ascending
+            int q = m < kExportMax ? m : kExportMax;
+            if (q == kExportMax && oj >= js[kExportMax - 1]) continue;
+            if (q == kExportMax) q = kExportMax - 1;
+            while (q > 0 && js[q - 1] > oj) { js[q] = js[q - 1]; --q; }
+            js[q] = oj;
+            if (m < kExportMax) ++m;
+        }
+        for (int t = 0; t < m; ++t) {
+            if (base + t < cap) {
+                iap[2 * (base + t)] = oi;
+                iap[2 * (base + t) + 1] = js[t];
+            }
+        }
+        if (m < kExportMax) break;
+        base += m;
+        last = js[m - 1];
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+separations_kernel(double Lx, double Ly, double Lz, const int32_t *__restrict__ iap, int64_t nip,
+                   const double *__restrict__ r, const double *__restrict__ v,
+                   double *__restrict__ drij, double *__restrict__ rij, double *__restrict__ rsq,
+                   double *__restrict__ dv)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nip) return;
+    const size_t i = (size_t)iap[2 * k], j = (size_t)iap[2 * k + 1];
+    // neighbour_list.py:66-82
+    const double dx = min_image(__dsub_rn(r[3 * j], r[3 * i]), Lx, Lx / 2.);
+    const double dy = min_image(__dsub_rn(r[3 * j + 1], r[3 * i + 1]), Ly, Ly / 2.);
+    const double dz = min_image(__dsub_rn(r[3 * j + 2], r[3 * i + 2]), Lz, Lz / 2.);
+    const double s = rsq_exact(dx, dy, dz);
+    drij[3 * k] = dx; drij[3 * k + 1] = dy; drij[3 * k + 2] = dz;
+    rsq[k] = s;
+    rij[k] = sqrt(s);
+    dv[3 * k] = v[3 * j] - v[3 * i];
+    dv[3 * k + 1] = v[3 * j + 1] - v[3 * i + 1];
+    dv[3 * k + 2] = v[3 * j + 2] - v[3 * i + 2];
+}
+
+__global__ void __launch_bounds__(kBlock)
+pair_kernels_kernel(const int32_t *__restrict__ iap, int64_t nip, const double *__restrict__ rij,
+                    const double *__restrict__ drij, const double *__restrict__ h,
+                    double *__restrict__ wij, double *__restrict__ dwij)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nip) return;
+    const double hh = h[iap[2 * k]];                       // properties.py:88
+    double rr = rij[k];
+    if (rr < 0) rr = fabs(rr);                             // spkernel.py:104-105
+    const double q = lucy_norm3(hh);
+    double w = 0.0, gx = 0.0, gy = 0.0, gz = 0.0;
+    if (rr < hh) {
+        const double t = 1. - rr / hh;
+        w = q * (1 + 3. * rr / hh) * (t * t * t);          // spkernel.py:107
+        if (rr != 0) {
+            const double h2 = hh * hh;
+            const double f = q * ((-12. / (h2 * h2)) * (rr * rr * rr) + (24. / (h2 * hh)) * (rr * rr)
+                                  - (12. * rr / h2));      // spkernel.py:113-114
+            gx = f * drij[3 * k] / rr;
+            gy = f * drij[3 * k + 1] / rr;
+            gz = f * drij[3 * k + 2] / rr;
+        }
+    }
+    wij[k] = w;
+    dwij[3 * k] = gx; dwij[3 * k + 1] = gy; dwij[3 * k + 2] = gz;
+}
+
+__global__ void __launch_bounds__(kBlock)
+ponder_kernel(const double *__restrict__ r_old, const double *__restrict__ r, int n,
+              sph_status *__restrict__ status)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0;
+    if (i < n) {
+        // neighbour_list.py:230-231
+        const double a = r_old[3 * (size_t)i] - r[3 * (size_t)i];
+        const double b = r_old[3 * (size_t)i + 1] - r[3 * (size_t)i + 1];
+        const double c = r_old[3 * (size_t)i + 2] - r[3 * (size_t)i + 2];
+        s = rsq_exact(a, b, c);
+        if (!(s >= 0.0)) s = 0.0;                          // NaN never triggers `dsq > tol`
+    }
+    unsigned long long bits = (unsigned long long)__double_as_longlong(s);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const unsigned long long t = __shfl_xor_sync(0xffffffffu, bits, o);
+        bits = t > bits ? t : bits;
+    }
+    if ((threadIdx.x & 31) == 0 && bits > *(volatile unsigned long long *)&status->dsq_max_bits)
+        atomicMax(&status->dsq_max_bits, bits);
+}
+
+__global__ void ponder_decide_kernel(sph_status *status, double tol_sq)
+{
+    const double dsq = __longlong_as_double((long long)status->dsq_max_bits);
+    status->rebuild = dsq > tol_sq ? 1u : 0u;              // neighbour_list.py:233-234
+}
+
+__global__ void status_reset_kernel(sph_status *status)
+{
+    if (threadIdx.x < sizeof(sph_status) / 4) reinterpret_cast<uint32_t *>(status)[threadIdx.x] = 0u;
+}
+
+__global__ void __launch_bounds__(kBlock)
+axpy_kernel(double *__restrict__ x, const double *__restrict__ a, const double *__restrict__ b,
+            double s, int64_t len)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) x[i] = a[i] + s * b[i];
+}
+
+__global__ void __launch_bounds__(kBlock)
+box_kernel(double Lx, double Ly, double Lz, int kind, double *__restrict__ r, double *__restrict__ v, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double L[3] = {Lx, Ly, Lz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double x = r[3 * (size_t)i + d];
+        if (kind == 0) {                                   // box.py:53-73 MirrorBox
+            if (x > L[d]) { x = L[d]; v[3 * (size_t)i + d] = -v[3 * (size_t)i + d]; }
+            if (x < 0) { x = 0; v[3 * (size_t)i + d] = -v[3 * (size_t)i + d]; }
+        } else {                                           // box.py:35-47 PeriodicBox
+            if (x > L[d]) x = 0;
+            if (x < 0) x = L[d];
+        }
+        r[3 * (size_t)i + d] = x;
+    }
+}
+
+inline int blocks_for(int64_t n, int per) { return (int)((n + per - 1) / per); }
+
+inline int launch_status()
+{
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPH_OK : (int)e;
+}
+
+int g_sm_count = 0;
+
+int sm_count()
+{
+    if (!g_sm_count) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char *sph_version(void) { return "pyticles_b200 0.1 (sm_100a, abi 1)"; }
+
+int64_t sph_scan_tmp_elems(uint32_t ncode)
+{
+    return ((int64_t)ncode + kScanTile - 1) / kScanTile + 2;
+}
+
+int64_t sph_nbr_elems(int32_t n, int32_t max_nbrs)
+{
+    return (((int64_t)n + 31) / 32) * 32 * (int64_t)max_nbrs;
+}
+
+int sph_grid_plan(const double box[3], double cutoff, double tolerance, int64_t n_hint,
+                  const double *occ_lo, const double *occ_hi, sph_grid *g)
+{
+    if (!box || !g) return SPH_E_BADARG;
+    const double thr = cutoff * cutoff + tolerance * tolerance;    // neighbour_list.py:155-157
+    if (!(thr > 0.0) || !isfinite(thr)) return SPH_E_GRID;
+    const double rl = sqrt(thr);
+    const double wmin = rl * (1.0 + 1.0 / 1048576.0);
+    int ncmax[3];
+    for (int d = 0; d < 3; ++d) {
+        if (!(box[d] > 0.0) || !isfinite(box[d])) return SPH_E_GRID;
+        g->box[d] = box[d];
+        double q = floor(box[d] / wmin);
+        if (q < 1.0) q = 1.0;
+        if (q > 4096.0) q = 4096.0;
+        ncmax[d] = (int)q;
+        g->nc[d] = ncmax[d];
+    }
+    g->thr = thr;
+    // keep the cell table O(n): coarsen the dimensions whose cells are mostly empty
+    if (n_hint > 0) {
+        const double budget = fmax(32768.0, 2.0 * (double)n_hint);
+        for (int iter = 0; iter < 64; ++iter) {
+            const double cells = (double)g->nc[0] * g->nc[1] * g->nc[2];
+            if (cells <= budget) break;
+            int best = -1;
+            double best_waste = 1.0;
+            for (int d = 0; d < 3; ++d) {
+                if (g->nc[d] <= 3) continue;
+                double occ = g->nc[d];
+                if (occ_lo && occ_hi) {
+                    const double w = box[d] / g->nc[d];
+                    occ = floor((occ_hi[d] - occ_lo[d]) / w) + 2.0;
+                    if (!(occ >= 1.0)) occ = 1.0;
+                    if (occ > g->nc[d]) occ = g->nc[d];
+                }
+                const double waste = g->nc[d] / occ;
+                if (waste > best_waste * 1.5) { best_waste = waste; best = d; }
+            }
+            if (best < 0) break;
+            g->nc[best] = g->nc[best] / 2 < 3 ? 3 : g->nc[best] / 2;
+        }
+    }
+    double wmax = 0.0;
+    int bits[3], total_bits = 0;
+    for (int d = 0; d < 3; ++d) {
+        g->w[d] = box[d] / g->nc[d];
+        g->inv_w[d] = g->nc[d] / box[d];
+        g->lo[d] = 0;
+        g->ncl[d] = g->nc[d];
+        g->wrap[d] = 1;
+        if (g->w[d] > wmax) wmax = g->w[d];
+        bits[d] = 0;
+        while ((1 << bits[d]) < g->ncl[d]) ++bits[d];
+        total_bits += bits[d];
+    }
+    if (total_bits > 30) return SPH_E_TOOBIG;
+    // generalised Morton code: deal the bits of x, y, z round-robin while each has bits left
+    g->mask[0] = g->mask[1] = g->mask[2] = 0;
+    int used[3] = {0, 0, 0}, out = 0;
+    while (out < total_bits)
+        for (int d = 0; d < 3; ++d)
+            if (used[d] < bits[d]) { g->mask[d] |= 1u << out; ++out; ++used[d]; }
+    g->ncode = 1u << total_bits;
+    // fp32 pre-filter band.  Cell-relative coordinates carry an absolute error of at most
+    // ~4 * 2^-24 * wmax per component after the shift and the subtraction; rsq inherits
+    // 2*sqrt(3)*rl*err + 3*err^2 plus ~8*2^-24 relative from its own arithmetic.  Use 4x that.
+    const double u = 1.0 / 16777216.0;
+    const double err = 8.0 * u * wmax;
+    const double band = 4.0 * (2.0 * 1.7320508 * (rl + err) * err + 3.0 * err * err + 8.0 * u * thr);
+    float tin = (float)(thr - band), tout = (float)(thr + band);
+    tin = nextafterf(tin, -INFINITY);
+    tout = nextafterf(tout, INFINITY);
+    if (!(tin > 0.0f)) tin = 0.0f;
+    g->thr_in = tin;
+    g->thr_out = tout;
+    for (int k = 0; k < 4; ++k) g->reserved[k] = 0;
+    return SPH_OK;
+}
+
+int sph_grid_restrict_x(sph_grid *g, int32_t first_layer, int32_t n_layers)
+{
+    if (!g || n_layers <= 0 || n_layers > g->nc[0]) return SPH_E_BADARG;
+    first_layer %= g->nc[0];
+    if (first_layer < 0) first_layer += g->nc[0];
+    g->lo[0] = first_layer;
+    g->ncl[0] = n_layers;
+    g->wrap[0] = (n_layers == g->nc[0]) ? 1 : 0;
+    int bits[3], total_bits = 0;
+    for (int d = 0; d < 3; ++d) {
+        bits[d] = 0;
+        while ((1 << bits[d]) < g->ncl[d]) ++bits[d];
+        total_bits += bits[d];
+    }
+    g->mask[0] = g->mask[1] = g->mask[2] = 0;
+    int used[3] = {0, 0, 0}, out = 0;
+    while (out < total_bits)
+        for (int d = 0; d < 3; ++d)
+            if (used[d] < bits[d]) { g->mask[d] |= 1u << out; ++out; ++used[d]; }
+    g->ncode = 1u << total_bits;
+    return SPH_OK;
+}
+
+int sph_status_reset(sph_status *d_status, void *stream)
+{
+    if (!d_status) return SPH_E_BADARG;
+    status_reset_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_status);
+    return launch_status();
+}
+
+int sph_exclusive_scan_u32(const uint32_t *d_in, uint32_t *d_out, uint32_t *d_tmp, int64_t n,
+                           void *stream)
+{
+    if (!d_in || !d_out || !d_tmp || n <= 0) return SPH_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t ntiles = (n + kScanTile - 1) / kScanTile;
+    scan_tile_sums<<<(unsigned)ntiles, kBlock, 0, s>>>(d_in, n, d_tmp);
+    scan_tile_offsets<<<1, kBlock, 0, s>>>(d_tmp, ntiles);
+    scan_tile_apply<<<(unsigned)ntiles, kBlock, 0, s>>>(d_in, d_out, n, d_tmp, ntiles);
+    return launch_status();
+}
+
+int sph_cells_build(const sph_grid *g, const sph_buffers *b, const double *d_r, void *stream)
+{
+    if (!g || !b || !d_r || b->n < 0) return SPH_E_BADARG;
+    if (!b->cell_count || !b->cell_start || !b->scan_tmp || !b->code || !b->rank || !b->perm || !b->status)
+        return SPH_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(b->cell_count, 0, sizeof(uint32_t) * (size_t)g->ncode, s);
+    if (b->n > 0)
+        bin_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, s>>>(*g, d_r, b->n, b->cell_count, b->code,
+                                                               b->rank, b->status);
+    int rc = sph_exclusive_scan_u32(b->cell_count, b->cell_start, b->scan_tmp, g->ncode, stream);
+    if (rc != SPH_OK) return rc;
+    if (b->n > 0) {
+        scatter_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, s>>>(b->n, b->code, b->rank, b->cell_start, b->perm);
+        cell_sort_kernel<<<blocks_for(g->ncode, kBlock), kBlock, 0, s>>>(g->ncode, b->cell_start, b->perm);
+    }
+    return launch_status();
+}
+
+int sph_gather(const sph_grid *g, const sph_buffers *b, const double *d_r, const double *d_v,
+               const double *d_m, void *stream)
+{
+    if (!g || !b || !d_r || !d_v || !d_m || !b->pos4 || !b->vel4 || !b->rel4 || !b->perm) return SPH_E_BADARG;
+    if (b->n > 0)
+        gather_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+            *g, b->n, b->perm, d_r, d_v, d_m, b->pos4, b->vel4, b->rel4);
+    return launch_status();
+}
+
+int sph_nlist_build(const sph_grid *g, const sph_buffers *b, void *stream)
+{
+    if (!g || !b || !b->nbr || !b->cnt || !b->rel4 || !b->pos4 || !b->cell_start || !b->status) return SPH_E_BADARG;
+    if (b->max_nbrs <= 0) return SPH_E_BADARG;
+    if (b->n == 0) return SPH_OK;
+    static bool configured = false;
+    const size_t smem = sizeof(float4) * kNlWin * kNlWarps;
+    if (!configured) {
+        cudaFuncSetAttribute(nlist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    const int64_t warps_needed = g->ncode;
+    int64_t blocks = (warps_needed + kNlWarps - 1) / kNlWarps;
+    const int64_t cap = (int64_t)sm_count() * 3 * 8;       // a few resident waves, grid-stride beyond
+    if (blocks > cap) blocks = cap;
+    nlist_kernel<<<(unsigned)blocks, kNlWarps * 32, smem, (cudaStream_t)stream>>>(
+        *g, b->n, b->max_nbrs, b->cell_start, b->rel4, b->pos4, b->nbr, b->cnt, b->status);
+    return launch_status();
+}
+
+int sph_density_eos(const sph_grid *g, const sph_buffers *b, const sph_eos *eos,
+                    const double *d_h_orig, int h_uniform, int list_fresh, int use_hlr,
+                    double *d_rho, double *d_p, double *d_pco, double *d_u, double *d_t, void *stream)
+{
+    if (!g || !b || !eos || !d_h_orig || !d_rho) return SPH_E_BADARG;
+    if (!use_hlr && (!d_p || !d_pco || !d_u || !d_t)) return SPH_E_BADARG;
+    if (b->n == 0) return SPH_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nb = blocks_for(b->n, kBlock);
+    if (h_uniform)
+        density_kernel<true><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm,
+                                                   b->nbr, b->cnt, b->status, d_h_orig, *eos, list_fresh,
+                                                   use_hlr, d_rho, d_p, d_pco, d_u, d_t);
+    else
+        density_kernel<false><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm,
+                                                    b->nbr, b->cnt, b->status, d_h_orig, *eos, list_fresh,
+                                                    use_hlr, d_rho, d_p, d_pco, d_u, d_t);
+    return launch_status();
+}
+
+int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, const double *d_rho,
+              const double *d_h_orig, int h_uniform, int list_fresh, double fcutoff, int dim,
+              double *d_vdot, double *d_udot, void *stream)
+{
+    if (!g || !b || !d_h_orig || !d_vdot || !d_udot) return SPH_E_BADARG;
+    if ((d_press == nullptr) != (d_rho == nullptr)) return SPH_E_BADARG;
+    if (b->n == 0) return SPH_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nb = blocks_for(b->n, kBlock);
+    if (d_press)
+        pressure_term_kernel<<<nb, kBlock, 0, s>>>(b->n, b->perm, d_press, d_rho, b->vel4);
+    const double fcutsq = fcutoff * fcutoff;                // forces.py:36
+    if (h_uniform)
+        force_kernel<true><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr,
+                                                 b->cnt, b->status, d_h_orig, list_fresh, fcutsq, dim, d_vdot, d_udot);
+    else
+        force_kernel<false><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr,
+                                                  b->cnt, b->status, d_h_orig, list_fresh, fcutsq, dim, d_vdot, d_udot);
+    return launch_status();
+}
+
+int sph_pairs_count(const sph_buffers *b, uint32_t *d_row_count, void *stream)
+{
+    if (!b || !d_row_count) return SPH_E_BADARG;
+    if (b->n > 0)
+        pairs_count_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+            b->n, b->max_nbrs, b->perm, b->nbr, b->cnt, d_row_count);
+    return launch_status();
+}
+
+int sph_pairs_fill(const sph_buffers *b, const uint32_t *d_row_start, int32_t *d_iap, int64_t cap_pairs, void *stream)
+{
+    if (!b || !d_row_start || (!d_iap && cap_pairs > 0)) return SPH_E_BADARG;
+    if (b->n > 0 && cap_pairs > 0)
+        pairs_fill_kernel<<<blocks_for(b->n, 128), 128, 0, (cudaStream_t)stream>>>(
+            b->n, b->max_nbrs, b->perm, b->nbr, b->cnt, d_row_start, d_iap, cap_pairs);
+    return launch_status();
+}
+
+int sph_separations(const double box[3], const int32_t *d_iap, int64_t nip, const double *d_r,
+                    const double *d_v, double *d_drij, double *d_rij, double *d_rsq, double *d_dv, void *stream)
+{
+    if (!box || nip < 0) return SPH_E_BADARG;
+    if (nip == 0) return SPH_OK;
+    if (!d_iap || !d_r || !d_v || !d_drij || !d_rij || !d_rsq || !d_dv) return SPH_E_BADARG;
+    separations_kernel<<<blocks_for(nip, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+        box[0], box[1], box[2], d_iap, nip, d_r, d_v, d_drij, d_rij, d_rsq, d_dv);
+    return launch_status();
+}
+
+int sph_pair_kernels(const int32_t *d_iap, int64_t nip, const double *d_rij, const double *d_drij,
+                     const double *d_h, double *d_wij, double *d_dwij, void *stream)
+{
+    if (nip < 0) return SPH_E_BADARG;
+    if (nip == 0) return SPH_OK;
+    if (!d_iap || !d_rij || !d_drij || !d_h || !d_wij || !d_dwij) return SPH_E_BADARG;
+    pair_kernels_kernel<<<blocks_for(nip, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+        d_iap, nip, d_rij, d_drij, d_h, d_wij, d_dwij);
+    return launch_status();
+}
+
+int sph_compress(const sph_grid *g, const sph_buffers *b, void *stream)
+{
+    if (!g || !b || !b->nbr || !b->cnt || !b->pos4) return SPH_E_BADARG;
+    if (b->n > 0)
+        compress_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+            *g, b->n, b->max_nbrs, b->pos4, b->nbr, b->cnt);
+    return launch_status();
+}
+
+int sph_ponder_rebuild(const double *d_r_old, const double *d_r, int32_t n, double tol_sq,
+                       sph_status *d_status, void *stream)
+{
+    if (!d_r_old || !d_r || !d_status || n < 0) return SPH_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(&d_status->dsq_max_bits, 0, sizeof(unsigned long long), s);
+    if (n > 0) ponder_kernel<<<blocks_for(n, kBlock), kBlock, 0, s>>>(d_r_old, d_r, n, d_status);
+    ponder_decide_kernel<<<1, 1, 0, s>>>(d_status, tol_sq);
+    return launch_status();
+}
+
+int sph_axpy(double *d_x, const double *d_a, const double *d_b, double sc, int64_t len, void *stream)
+{
+    if (len < 0 || (len > 0 && (!d_x || !d_a || !d_b))) return SPH_E_BADARG;
+    if (len > 0) axpy_kernel<<<blocks_for(len, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_x, d_a, d_b, sc, len);
+    return launch_status();
+}
+
+int sph_box_apply(const double box[3], int kind, double *d_r, double *d_v, int32_t n, void *stream)
+{
+    if (!box || n < 0 || (n > 0 && (!d_r || !d_v))) return SPH_E_BADARG;
+    if (n > 0) box_kernel<<<blocks_for(n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(box[0], box[1], box[2], kind, d_r, d_v, n);
+    return launch_status();
+}
+
+}  // extern "C"

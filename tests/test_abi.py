@@ -1,0 +1,107 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/pyticles_b200.h
+declares; the host-side grid planner (no GPU work) behaves."""
+import ctypes
+import math
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "pyticles_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sph_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from pyticles_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def test_exports_every_declared_symbol(lib):
+    from pyticles_b200 import _lib
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+        assert n in _lib.SIGNATURES, "no ctypes signature for " + n
+    assert b"sm_100a" in lib.sph_version()
+
+
+def test_struct_layout_matches_header(lib):
+    from pyticles_b200 import _lib
+    assert ctypes.sizeof(_lib.SphStatus) == 64
+    assert ctypes.sizeof(_lib.SphGrid) == 8 * 10 + 4 * 12 + 4 * 3 + 4 + 4 + 4 + 16
+    assert ctypes.sizeof(_lib.SphEos) == 24
+
+
+def _plan(lib, box, cutoff, tol, n, lo=None, hi=None):
+    from pyticles_b200 import _lib
+    g = _lib.SphGrid()
+    rc = lib.sph_grid_plan(_lib.box3(box), cutoff, tol, n,
+                           _lib.box3(lo) if lo else None, _lib.box3(hi) if hi else None, ctypes.byref(g))
+    return rc, g
+
+
+def test_grid_plan_cells_cover_list_radius(lib):
+    for box, cutoff, tol in [((256., 256., 256.), 2.0, 0.0), ((20., 20., 20.), 2.0, 1.0),
+                             ((6., 6., 6.), 2.0, 1.0), ((5., 5., 1.), 10.0, 2.0), ((11., 9.5, 7.25), 2.0, 1.0)]:
+        rc, g = _plan(lib, box, cutoff, tol, 1000)
+        assert rc == 0
+        rl = math.sqrt(cutoff ** 2 + tol * tol)
+        assert g.thr == cutoff ** 2 + tol * tol
+        codes = 1
+        for d in range(3):
+            assert g.nc[d] >= 1 and g.ncl[d] == g.nc[d] and g.wrap[d] == 1
+            assert g.w[d] * g.nc[d] == pytest.approx(box[d], rel=1e-15)
+            assert g.nc[d] == 1 or g.w[d] >= rl * (1 + 2.0 ** -21)
+            codes *= 1 << max(0, (g.nc[d] - 1).bit_length())
+        assert g.ncode == codes
+        assert g.mask[0] | g.mask[1] | g.mask[2] == g.ncode - 1
+        assert g.mask[0] & g.mask[1] == 0 and g.mask[1] & g.mask[2] == 0 and g.mask[0] & g.mask[2] == 0
+        assert g.thr_in < g.thr < g.thr_out
+
+
+def test_grid_plan_coarsens_empty_dimension(lib):
+    rc, g = _plan(lib, (1024., 1024., 1024.), 2.0, 0.0, 1 << 20, (0.4, 0.4, 0.4), (1023.6, 1023.6, 0.6))
+    assert rc == 0
+    assert g.nc[0] == g.nc[1] == 511 or g.nc[0] == g.nc[1] == 512
+    assert 3 <= g.nc[2] <= 32
+    assert g.ncode <= 8 * (1 << 20)
+
+
+def test_grid_plan_rejects_bad_input(lib):
+    assert _plan(lib, (0., 5., 5.), 2.0, 1.0, 10)[0] == -2
+    assert _plan(lib, (5., 5., 5.), 0.0, 0.0, 10)[0] == -2
+    assert _plan(lib, (5., 5., float("nan")), 2.0, 1.0, 10)[0] == -2
+
+
+def test_slab_restriction(lib):
+    rc, g = _plan(lib, (512., 256., 256.), 2.0, 0.0, 1 << 24)
+    assert rc == 0
+    nc0 = g.nc[0]
+    assert lib.sph_grid_restrict_x(ctypes.byref(g), nc0 - 1, 10) == 0
+    assert g.lo[0] == nc0 - 1 and g.ncl[0] == 10 and g.wrap[0] == 0 and g.nc[0] == nc0
+    assert lib.sph_grid_restrict_x(ctypes.byref(g), 0, nc0 + 1) == -1
+
+
+def test_no_gpu_calls_fail_cleanly(lib):
+    # argument validation happens before any launch, so this is safe without a device
+    assert lib.sph_cells_build(None, None, None, None) == -1
+    assert lib.sph_axpy(None, None, None, 1.0, 4, None) == -1
+    assert lib.sph_separations(None, None, 0, None, None, None, None, None, None, None) == -1
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "pyticles_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+                assert "sph_oracle" not in text, f
