@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the SPH step hot path (BASELINE.json: "SPH particle-updates/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c4|small] [--impl reference]
+
+One "step" = one derivative evaluation of the hot path over one synthetic lattice-plus-jitter
+box: cell list + Morton reorder + neighbour pass + density/EOS pass +
+force pass.  `value` = particles * steps / time with inputs resident in HBM; `e2e` = the same
+through the public API with HOST buffers (pinned H2D of r, v, m, h, t and D2H of rho, p, vdot,
+udot every step).  Prints ONE JSON line (rank 0).
+
+Workloads (number density 1, h = cutoff = 2.0, tolerance 0, force cutoff 5, EOS a=2 b=.5 kb=1):
+    c3     3-D 256^3 = 16 777 216 particles on ONE GPU (BASELINE configs[2]); N>1 keeps 16 Mi per GPU
+           (weak scaling: the box grows along x, slab-decomposed; 4 GPUs = the 64 Mi box of configs[3])
+    c2     2-D sheet 1024x1024x1 in a 1024-deep box (configs[1])
+    c4     3-D 512x512x256 = 64 Mi particles in total, strong-scaled over the GPUs (configs[3])
+    small  3-D 64^3 (quick functional run)
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, built from the
+unmodified reference sources by oracle/make_ref.py) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "SPH particle-updates/s"
+UNIT = "particle-updates/s"
+SEED = 20263
+
+WORKLOADS = {
+    #        per-GPU lattice (nx, ny, nz), box z override, scaling
+    "c3": dict(dims=(256, 256, 256), zbox=None, scaling="weak",
+               name="3D periodic SPH box 256^3 (16 Mi particles) per GPU, fixed h"),
+    "c2": dict(dims=(1024, 1024, 1), zbox=1024.0, scaling="weak",
+               name="2D periodic SPH sheet 1024x1024 (1 Mi particles) per GPU in a 1024-deep box"),
+    "c4": dict(dims=(512, 512, 256), zbox=None, scaling="strong",
+               name="3D periodic SPH box 512x512x256 (64 Mi particles) in total"),
+    "small": dict(dims=(64, 64, 64), zbox=None, scaling="weak", name="3D periodic SPH box 64^3 per GPU"),
+}
+H, CUTOFF, TOL, FCUT = 2.0, 2.0, 0.0, 5.0
+EOS = (2.0, 0.5, 1.0)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples = []
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.samples:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for k, nm in enumerate(names):
+                if len(f) > 3 + k and f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ synthetic input
+def lattice_on_device(dims, x0, device, seed):
+    """(i+.5, j+.5, k+.5) + U(-.1,.1), v ~ U(-.05,.05); x fastest; lattice column offset x0."""
+    import torch
+    nx, ny, nz = dims
+    n = nx * ny * nz
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    idx = torch.arange(n, device=device, dtype=torch.int64)
+    r = torch.empty((n, 3), dtype=torch.float64, device=device)
+    r[:, 0] = (idx % nx + x0).to(torch.float64) + 0.5
+    r[:, 1] = ((idx // nx) % ny).to(torch.float64) + 0.5
+    r[:, 2] = (idx // (nx * ny)).to(torch.float64) + 0.5
+    del idx
+    r += (torch.rand((n, 3), dtype=torch.float64, device=device, generator=g) - 0.5) * 0.2
+    v = (torch.rand((n, 3), dtype=torch.float64, device=device, generator=g) - 0.5) * 0.1
+    return r, v
+
+
+# ------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own CPU path (oracle/_ref): ospana.py wiring -- VerletList + c_forces.SpamForce
+    (which computes spam_properties itself) driven by SmoothParticleSystem.derivatives()."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    wl = WORKLOADS[args.workload]
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    kind = "reference"
+    side = (12, 12, 12) if wl["dims"][2] > 1 else (40, 40, 1)
+    from oracle import oracle as O
+    r, v, box = O.lattice_workload(side[0], side[1], side[2], seed=SEED)
+    if wl["zbox"]:
+        box = (box[0], box[1], float(side[0]))
+    n = r.shape[0]
+    sample = "%dx%dx%d lattice-plus-jitter box (n=%d) of the same workload, list built once, %s" % (
+        side[0], side[1], side[2], n, "then timed derivative evaluations (separations + properties + force)")
+    step = None
+    if os.path.isdir(ref_dir) and any(f.startswith("particles.") for f in os.listdir(ref_dir)):
+        sys.path.insert(0, ref_dir)
+        import c_forces
+        import neighbour_list
+        import particles
+        p = particles.SmoothParticleSystem(n, d=3, maxn=n, xmax=box[0], ymax=box[1], zmax=box[2],
+                                           hshort=H, hlong=2 * H)
+        p.r[:, :] = r
+        p.v[:, :] = v
+        nl = neighbour_list.VerletList(p, cutoff=CUTOFF, tolerance=TOL)
+        p.nlists.append(nl)
+        p.nl_default = nl
+        p.forces.append(c_forces.SpamForce(p, nl))
+        nl.build()                     # O(n^2) pure Python, once, untimed (the reference never rebuilds)
+        step = p.derivatives
+    else:
+        kind = "port"
+        from oracle import c_oracle as C
+        m, h, t = np.ones(n), np.full(n, H), np.ones(n)
+        bx = np.array(box)
+
+        def step():
+            C.sph_step(r, v, m, h, t, bx, CUTOFF, TOL, FCUT)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+           "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": {"workload": wl["name"], "sample": sample},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def cpu_baseline():
+    """The oracle port (scalar C, 1 core) on a bounded sample of the workload, ~10-20 s."""
+    import numpy as np
+    from oracle import c_oracle as C
+    from oracle import oracle as O
+    side = (64, 64, 32)
+    r, v, box = O.lattice_workload(*side, seed=SEED)
+    n = r.shape[0]
+    m, h, t, bx = np.ones(n), np.full(n, H), np.ones(n), np.array(box)
+    C.sph_step(r, v, m, h, t, bx, CUTOFF, TOL, FCUT)
+    reps, t0 = 0, time.perf_counter()
+    while reps < 3 or time.perf_counter() - t0 < 8.0:
+        C.sph_step(r, v, m, h, t, bx, CUTOFF, TOL, FCUT)
+        reps += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * reps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%dx%dx%d box (n=%d), %d full evaluations (cell-list build + separations + density/EOS "
+                      "+ force) of oracle/sph_oracle.c" % (side[0], side[1], side[2], n, reps)}
+
+
+# ------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU path")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    from pyticles_b200 import stepper
+    wl = WORKLOADS[args.workload]
+    sim = stepper.make_bench_system(wl, world, rank, device, SEED, H, CUTOFF, TOL, FCUT, EOS)
+    n_local, n_total = sim.n_owned, sim.n_total
+
+    for _ in range(args.warmup):
+        sim.evaluate()
+    sim.check()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    sim.reset_pass_timers()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        sim.evaluate(timed=True)
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.time()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tm = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    sim.check()
+    passes = sim.pass_times()           # per-pass mean ms over the timed steps (CUDA events)
+    pairs = sim.pairs_per_particle()
+
+    e2e = None
+    if not args.no_e2e:
+        e2e = sim.run_e2e(args.steps, max(1, min(args.warmup, 3)))
+        if world > 1:
+            tm = torch.tensor([e2e["ms"]], dtype=torch.float64, device=device)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            e2e["ms"] = float(tm.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    value = n_total * args.steps / (ms * 1e-3)
+    # algorithmic bytes per particle per launch (SURVEY.md section 8d / DESIGN.md)
+    alg = {"cells+reorder": 24.0 + 2 * 72.0, "neighbour": 24.0 + 8.0 * pairs, "density": 80.0, "force": 112.0}
+    pass_out = {}
+    for k, t_ms in passes.items():
+        if k in alg and t_ms > 0:
+            gbs = alg[k] * n_local / (t_ms * 1e-3) / 1e9
+            pass_out[k] = {"ms": round(t_ms, 4), "alg_bytes_per_particle": round(alg[k], 1),
+                           "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        else:
+            pass_out[k] = {"ms": round(t_ms, 4)}
+    dom = max((k for k in pass_out if k in alg), key=lambda k: pass_out[k]["ms"])
+    step_bytes = (216.0 + 8.0 * pairs) * n_local
+    roof = {"bound": "hbm", "kernel": sim.kernel_names[dom], "pass": dom,
+            "achieved": pass_out[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": pass_out[dom]["frac"], "traffic": sim.ncu_traffic.get(dom),
+            "peak_source": peak_src,
+            "whole_step": {"alg_bytes_per_particle": round(216.0 + 8.0 * pairs, 1),
+                           "achieved_gbs": round(step_bytes / (ms / args.steps * 1e-3) / 1e9, 1),
+                           "frac": round(step_bytes / (ms / args.steps * 1e-3) / 1e9 / peak, 4)},
+            "passes": pass_out, "pairs_per_particle": round(pairs, 3),
+            "pairs_per_s": round(pairs * value, 1)}
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+           "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": wl["name"], "particles_total": n_total, "particles_per_gpu": n_local,
+                      "h": H, "cutoff": CUTOFF, "tolerance": TOL, "force_cutoff": FCUT,
+                      "parallelism": "single GPU" if world == 1 else "x-slab decomposition over %d GPUs, NCCL halo exchange" % world,
+                      "l2": "inputs larger than L2 (no flush)" if n_local * 350 > 3 * 126e6 else "working set near L2 size; no flush",
+                      "max_nbrs": sim.max_nbrs},
+           "roofline": roof, "gpu_launches": sim.launches_per_eval * args.steps}
+    if clocks:
+        out["clocks"] = clocks
+    if e2e:
+        out["e2e"] = {"value": n_total * e2e["steps"] / (e2e["ms"] * 1e-3), "unit": UNIT,
+                      "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                      "ms_per_step": e2e["ms"] / e2e["steps"]}
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

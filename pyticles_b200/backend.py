@@ -104,17 +104,26 @@ class NeighbourBackend(object):
         b.status = _ptr(self.status_t)
 
     # ------------------------------------------------------------------ the hot path
-    def cells_and_list(self, r, v, m, check_overflow=True):
-        """sph_status_reset + sph_cells_build + sph_gather + sph_nlist_build on the current stream."""
+    def cells_and_gather(self, r, v, m):
+        """sph_status_reset + sph_cells_build + sph_gather on the current stream."""
         L, g, b, s = self.lib, ctypes.byref(self.grid), ctypes.byref(self.buf), _stream()
         _f64(r, "r"), _f64(v, "v"), _f64(m, "m")
         check(L.sph_status_reset(_ptr(self.status_t), s), "sph_status_reset")
         check(L.sph_cells_build(g, b, _ptr(r), s), "sph_cells_build")
         check(L.sph_gather(g, b, _ptr(r), _ptr(v), _ptr(m), s), "sph_gather")
-        check(L.sph_nlist_build(g, b, s), "sph_nlist_build")
+        self.built = False
+
+    def nlist(self):
+        """sph_nlist_build on the current stream (after cells_and_gather)."""
+        check(self.lib.sph_nlist_build(ctypes.byref(self.grid), ctypes.byref(self.buf), _stream()), "sph_nlist_build")
         self.built = True
         self.fresh = True
         self.press_ready = False
+
+    def cells_and_list(self, r, v, m, check_overflow=True):
+        """The whole neighbour build: cell list, Morton reorder, neighbour pass."""
+        self.cells_and_gather(r, v, m)
+        self.nlist()
         if check_overflow:
             self.resolve_overflow()
 

@@ -1,0 +1,155 @@
+"""Fused driver of one derivative evaluation of the hot path, as bench.py and long runs use it.
+
+`SphEvaluator.evaluate()` enqueues, on the current stream and without any host sync,
+    status reset -> cell list -> Morton gather -> neighbour pass -> density/EOS -> force
+for a SmoothParticleSystem, i.e. what SmoothParticleSystem.derivatives() does
+(particles.py:544-570) with the list rebuilt at every evaluation.  Neighbour-capacity overflow
+is detected from the device status block at the next `check()`.
+"""
+import torch
+
+from . import _lib, forces, neighbour_list, particles, properties
+from .array import parray
+
+# launches of OUR kernels per evaluation: status_reset, bin, scan x3, scatter, cell_sort,
+# gather, nlist, density, force  (cudaMemset of the cell counters and the two torch fills of
+# vdot/udot are not counted)
+LAUNCHES_PER_EVAL = 11
+
+
+class SphEvaluator(object):
+    kernel_names = {"cells+reorder": "bin_kernel+scan+scatter_kernel+cell_sort_kernel+gather_kernel",
+                    "neighbour": "nlist_kernel", "density": "density_kernel<true>", "force": "force_kernel<true>"}
+    ncu_traffic = {}
+
+    def __init__(self, p, nl, force, eos=(2.0, 0.5, 1.0)):
+        self.p, self.nl, self.force, self.eos = p, nl, force, eos
+        self.n_owned = p.n
+        self.n_total = p.n
+        self.launches_per_eval = LAUNCHES_PER_EVAL
+        self._events = []
+        self._planned = False
+
+    @property
+    def max_nbrs(self):
+        return self.nl.backend.K
+
+    def _plan(self):
+        p, nl = self.p, self.nl
+        be = nl.backend
+        box = (p.box.xmax, p.box.ymax, p.box.zmax)
+        be.plan(box, nl.cutoff_radius, nl.tolerance, p.n, p.r)
+        be.ensure(p.n)
+        self.h_uniform = properties._h_uniform(p, p.h)
+        self._planned = True
+
+    def evaluate(self, timed=False):
+        if not self._planned:
+            self._plan()
+        p, be = self.p, self.nl.backend
+        ev = None
+        if timed:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record()
+        be.cells_and_gather(p.r, p.v, p.m)
+        if timed:
+            ev[1].record()
+        be.nlist()
+        if timed:
+            ev[2].record()
+        p.vdot.zero_()
+        p.udot.zero_()
+        be.density_eos(self.eos, p.h, self.h_uniform, p.rho, p.p, p.pco, p.u, p.t)
+        if timed:
+            ev[3].record()
+        be.force(None, None, p.h, self.h_uniform, self.force.cutoff, 3, p.vdot, p.udot, reuse_press=True)
+        if timed:
+            ev[4].record()
+            self._events.append(ev)
+
+    def check(self):
+        """Sync and look at the status block; grow the neighbour capacity if it overflowed."""
+        torch.cuda.synchronize()
+        be = self.nl.backend
+        st = be.status()
+        if st.flags & _lib.SPH_F_NBR_OVERFLOW:
+            be.user_max_nbrs = None
+            be.ensure(be.n, K=int(st.max_count) + max(4, int(st.max_count) // 8))
+            self.evaluate()
+            return self.check()
+        if st.flags & _lib.SPH_F_OUT_OF_SLAB:
+            raise _lib.SphError("a particle left the local cell-layer range")
+        self.nl._built_for = (p_ver(self.p.r))
+        return st
+
+    def reset_pass_timers(self):
+        self._events = []
+
+    def pass_times(self):
+        names = ["cells+reorder", "neighbour", "density", "force"]
+        tot = dict.fromkeys(names, 0.0)
+        for ev in self._events:
+            for k, nm in enumerate(names):
+                tot[nm] += ev[k].elapsed_time(ev[k + 1])
+        k = max(1, len(self._events))
+        return {nm: tot[nm] / k for nm in names}
+
+    def pairs_per_particle(self):
+        return self.nl.backend.count_links() / 2.0 / max(1, self.n_owned)
+
+    # ------------------------------------------------------------------ end to end with host buffers
+    def run_e2e(self, steps, warmup):
+        """Every step: pinned-host r, v, m, h, t -> device; evaluate; rho, p, vdot, udot -> pinned host."""
+        p = self.p
+        ins = [p.r, p.v, p.m, p.h, p.t]
+        outs = [p.rho, p.p, p.vdot, p.udot]
+        h_in = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in ins]
+        h_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
+        h2d = sum(t.numel() * t.element_size() for t in ins)
+        d2h = sum(t.numel() * t.element_size() for t in outs)
+
+        def one():
+            for d, h in zip(ins, h_in):
+                d.as_subclass(torch.Tensor).copy_(h, non_blocking=True)
+            self.evaluate()
+            for d, h in zip(outs, h_out):
+                h.copy_(d.as_subclass(torch.Tensor), non_blocking=True)
+
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        return {"ms": e0.elapsed_time(e1), "steps": steps, "h2d": h2d, "d2h": d2h}
+
+
+def p_ver(t):
+    return (t.data_ptr(), t._version)
+
+
+def make_bench_system(wl, world, rank, device, seed, h, cutoff, tol, fcut, eos):
+    """Synthetic lattice-plus-jitter system of bench.py for this rank."""
+    if world > 1:
+        from . import distributed
+        return distributed.make_bench_system(wl, world, rank, device, seed, h, cutoff, tol, fcut, eos)
+    import bench
+    nx, ny, nz = wl["dims"]
+    n = nx * ny * nz
+    box = (float(nx), float(ny), float(wl["zbox"] or nz))
+    p = particles.SmoothParticleSystem(n, d=3, maxn=n, xmax=box[0], ymax=box[1], zmax=box[2], hshort=h,
+                                       hlong=2 * h, device=device)
+    r, v = bench.lattice_on_device((nx, ny, nz), 0, device, seed)
+    p.r = parray(r)
+    p.v = parray(v)
+    nl = neighbour_list.VerletList(p, cutoff=cutoff, tolerance=tol)
+    nl.defer_status = True
+    p.nlists.append(nl)
+    p.nl_default = nl
+    f = forces.SpamForce(p, nl, cutoff=fcut)
+    p.forces.append(f)
+    return SphEvaluator(p, nl, f, eos)
