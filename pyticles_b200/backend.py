@@ -133,6 +133,9 @@ class NeighbourBackend(object):
         st = self.status()
         while st.flags & _lib.SPH_F_NBR_OVERFLOW:
             need = int(st.max_count)
+            if need <= self.K or need > max(self.n - 1, 8):
+                raise _lib.SphError("neighbour pass reports %d neighbours for one of %d particles "
+                                    "(capacity %d): inconsistent status" % (need, self.n, self.K))
             self.user_max_nbrs = None
             self.ensure(self.n, K=need + max(4, need // 8))
             L, s = self.lib, _stream()

@@ -280,14 +280,22 @@ gather_kernel(const __grid_constant__ sph_grid g, int n, const int32_t *__restri
 }
 
 // ------------------------------------------------------------------ neighbour pass
-__device__ __forceinline__ float wrap32(float d, float L)
+__device__ __forceinline__ float wrap32(float d, float L, float half)
 {
-    const float half = 0.5f * L;
     if (d > half) d -= L;
     if (d < -half) d += L;
     return d;
 }
 
+constexpr int kNlIB = 4;             // particles of the cell tested per staged-candidate load
+
+// One warp per cell.  Lanes 0..26 look up the 27 surrounding cells; their particles (fp32
+// cell-relative positions, already shifted into this cell's frame) are staged in shared
+// memory; then every lane tests one staged candidate against kNlIB particles of the cell per
+// pass.  rsq32 < thr_in accepts, rsq32 >= thr_out rejects, the band in between (and every
+// candidate when a position lies outside [-L/4, 5L/4]) is decided by pair_exact.  Accepted
+// neighbours are compacted with a ballot into the particle's warp-transposed ELL row.
+template <bool SMALL>
 __global__ void __launch_bounds__(kNlWarps * 32)
 nlist_kernel(const __grid_constant__ sph_grid g, int n, int K,
              const uint32_t *__restrict__ cell_start, const float *__restrict__ rel4,
@@ -300,9 +308,12 @@ nlist_kernel(const __grid_constant__ sph_grid g, int n, int K,
     float4 *S = smem_cand + wib * kNlWin;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const bool fast = !(status->flags & (SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
+    // slow mode: nothing is accepted in fp32 and everything is "in the band"
+    const float thr_in = fast ? g.thr_in : -1.0f;
+    const float thr_out = fast ? g.thr_out : INFINITY;
     const float4 *rel = reinterpret_cast<const float4 *>(rel4);
-    const bool small_x = g.ncl[0] < 3, small_y = g.ncl[1] < 3, small_z = g.ncl[2] < 3;
     const float Lx = (float)g.box[0], Ly = (float)g.box[1], Lz = (float)g.box[2];
+    const bool small_x = SMALL && g.ncl[0] < 3, small_y = SMALL && g.ncl[1] < 3, small_z = SMALL && g.ncl[2] < 3;
     uint32_t local_max = 0;
 
     const uint32_t nwarps = gridDim.x * kNlWarps;
@@ -311,7 +322,6 @@ nlist_kernel(const __grid_constant__ sph_grid g, int n, int K,
         if (cs == ce) continue;
         const int cx = (int)pext32(c, g.mask[0]), cy = (int)pext32(c, g.mask[1]),
                   cz = (int)pext32(c, g.mask[2]);
-        // lane q < 27 owns neighbour cell q
         uint32_t nstart = 0, ncount = 0;
         float fx = 0.f, fy = 0.f, fz = 0.f;
         if (lane < 27) {
@@ -321,7 +331,7 @@ nlist_kernel(const __grid_constant__ sph_grid g, int n, int K,
             bool ok = true;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                if (g.ncl[d] >= 3) {
+                if (!SMALL || g.ncl[d] >= 3) {
                     int t = cc[d] + o[d];
                     if (t < 0 || t >= g.ncl[d]) {
                         if (g.wrap[d]) t += (t < 0) ? g.ncl[d] : -g.ncl[d];
@@ -354,57 +364,85 @@ nlist_kernel(const __grid_constant__ sph_grid g, int n, int K,
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t prefix = incl - ncount;
+        const uint32_t maxc = __reduce_max_sync(0xffffffffu, ncount);
 
         for (uint32_t wbase = 0; wbase < total; wbase += kNlWin) {
             __syncwarp();
-            for (int q = 0; q < 27; ++q) {
-                const uint32_t ct = __shfl_sync(0xffffffffu, ncount, q);
-                const uint32_t pf = __shfl_sync(0xffffffffu, prefix, q);
-                const uint32_t st = __shfl_sync(0xffffffffu, nstart, q);
-                const float sx = __shfl_sync(0xffffffffu, fx, q);
-                const float sy = __shfl_sync(0xffffffffu, fy, q);
-                const float sz = __shfl_sync(0xffffffffu, fz, q);
-                if (ct == 0 || pf + ct <= wbase || pf >= wbase + kNlWin) continue;
-                for (uint32_t t = lane; t < ct; t += 32) {
-                    const uint32_t s = pf + t;
-                    if (s >= wbase && s < wbase + kNlWin) {
-                        const float4 p = __ldg(rel + st + t);
-                        S[s - wbase] = make_float4(p.x + sx, p.y + sy, p.z + sz,
-                                                   __int_as_float((int)(st + t)));
-                    }
+            // every lane copies the particles of the neighbour cell it owns
+            for (uint32_t t = 0; t < maxc; ++t) {
+                const uint32_t s = prefix + t - wbase;          // wraps below the window: fails s < kNlWin
+                if (t < ncount && s < (uint32_t)kNlWin) {
+                    const float4 p = __ldg(rel + nstart + t);
+                    S[s] = make_float4(p.x + fx, p.y + fy, p.z + fz, __int_as_float((int)(nstart + t)));
                 }
             }
-            __syncwarp();
             const uint32_t nS = min((uint32_t)kNlWin, total - wbase);
-            for (uint32_t a = cs; a < ce; ++a) {
-                const float4 pi = __ldg(rel + a);
-                uint32_t cnt_i = wbase ? (uint32_t)cnt[a] : 0u;
-                int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
-                for (uint32_t s0 = 0; s0 < nS; s0 += 32) {
-                    const uint32_t s = s0 + lane;
-                    const bool valid = s < nS;
-                    const float4 cd = S[valid ? s : 0];
-                    float dx = cd.x - pi.x, dy = cd.y - pi.y, dz = cd.z - pi.z;
-                    if (small_x) dx = wrap32(dx, Lx);
-                    if (small_y) dy = wrap32(dy, Ly);
-                    if (small_z) dz = wrap32(dz, Lz);
-                    const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    const int j = __float_as_int(cd.w);
-                    const bool other = valid && (uint32_t)j != a;
-                    bool inside = other && fast && rsq < g.thr_in;
-                    const bool border = other && !inside && (!fast || rsq < g.thr_out);
-                    if (__any_sync(0xffffffffu, border)) {
-                        if (border) inside = pair_exact(g, pos4, (int)a, j);
-                    }
-                    const uint32_t mask = __ballot_sync(0xffffffffu, inside);
-                    if (inside) {
-                        const uint32_t pos = cnt_i + __popc(mask & lt_mask);
-                        if (pos < (uint32_t)K) row[(size_t)pos * 32] = j;
-                    }
-                    cnt_i += __popc(mask);
+            const uint32_t nSp = (nS + 31u) & ~31u;
+            // pad the last chunk with candidates at infinity: rsq = +inf fails every threshold
+            if (nS + lane < nSp) S[nS + lane] = make_float4(1.0e30f, 1.0e30f, 1.0e30f, __int_as_float(-1));
+            __syncwarp();
+            for (uint32_t a0 = cs; a0 < ce; a0 += kNlIB) {
+                float px[kNlIB], py[kNlIB], pz[kNlIB], tin[kNlIB], tout[kNlIB];
+                uint32_t cnt_i[kNlIB];
+                int self[kNlIB];
+                int32_t *row[kNlIB];
+#pragma unroll
+                for (int u = 0; u < kNlIB; ++u) {
+                    const bool act = a0 + u < ce;
+                    const uint32_t a = act ? a0 + u : ce - 1;
+                    const float4 pi = __ldg(rel + a);
+                    px[u] = pi.x; py[u] = pi.y; pz[u] = pi.z;
+                    tin[u] = act ? thr_in : -1.0f;                 // padding rows accept nothing ...
+                    tout[u] = act ? thr_out : -1.0f;               // ... and have no band
+                    self[u] = (int)a;
+                    cnt_i[u] = (wbase && act) ? (uint32_t)cnt[a] : 0u;
+                    row[u] = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
                 }
-                if (lane == 0) cnt[a] = (int32_t)cnt_i;
-                local_max = max(local_max, cnt_i);
+                for (uint32_t s0 = 0; s0 < nSp; s0 += 32) {
+                    const float4 cd = S[s0 + lane];
+                    const int j = __float_as_int(cd.w);
+                    bool in[kNlIB], band = false;
+#pragma unroll
+                    for (int u = 0; u < kNlIB; ++u) {
+                        float dx = cd.x - px[u], dy = cd.y - py[u], dz = cd.z - pz[u];
+                        if (SMALL) {
+                            if (small_x) dx = wrap32(dx, Lx, 0.5f * Lx);
+                            if (small_y) dy = wrap32(dy, Ly, 0.5f * Ly);
+                            if (small_z) dz = wrap32(dz, Lz, 0.5f * Lz);
+                        }
+                        const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        in[u] = rsq < tin[u] && j != self[u];
+                        band = band || (!in[u] && rsq < tout[u] && j != self[u]);
+                    }
+                    if (__any_sync(0xffffffffu, band)) {           // rare: decide in fp64
+#pragma unroll
+                        for (int u = 0; u < kNlIB; ++u) {
+                            float dx = cd.x - px[u], dy = cd.y - py[u], dz = cd.z - pz[u];
+                            if (SMALL) {
+                                if (small_x) dx = wrap32(dx, Lx, 0.5f * Lx);
+                                if (small_y) dy = wrap32(dy, Ly, 0.5f * Ly);
+                                if (small_z) dz = wrap32(dz, Lz, 0.5f * Lz);
+                            }
+                            const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            if (!in[u] && rsq < tout[u] && j != self[u] && j >= 0)
+                                in[u] = pair_exact(g, pos4, self[u], j);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kNlIB; ++u) {
+                        const uint32_t mask = __ballot_sync(0xffffffffu, in[u]);
+                        const uint32_t pos = cnt_i[u] + __popc(mask & lt_mask);
+                        if (in[u] && pos < (uint32_t)K) row[u][(size_t)pos * 32] = j;
+                        cnt_i[u] += __popc(mask);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kNlIB; ++u) {
+                    if (a0 + u < ce) {
+                        if (lane == 0) cnt[a0 + u] = (int32_t)cnt_i[u];
+                        local_max = max(local_max, cnt_i[u]);
+                    }
+                }
             }
         }
     }
@@ -438,38 +476,57 @@ __device__ __forceinline__ double lucy_norm3(double h)
     return 105. / (SPH_PI * 16. * (h * h * h));       // spkernel.py:99
 }
 
+constexpr int kRowU = 4;             // neighbours gathered per pipeline stage
+
 template <bool UNIFORM_H, bool WRAP>
 __device__ __forceinline__ double density_row(const sph_grid &g, const double *__restrict__ pos4,
                                               const int32_t *__restrict__ perm,
                                               const double *__restrict__ h_orig,
-                                              const int32_t *__restrict__ row, int count, int orig,
+                                              const int32_t *__restrict__ row, int count, int orig, int self,
                                               double ax, double ay, double az, double hinv, double qn)
 {
     double acc = 0.0;
     const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
-    for (int k = 0; k < count; ++k) {
-        const int j = row[(size_t)k * 32];
-        double bx, by, bz, bm;
-        load4(pos4 + 4 * (size_t)j, bx, by, bz, bm);
-        double dx = bx - ax, dy = by - ay, dz = bz - az;
-        if (WRAP) {
-            dx = min_image(dx, g.box[0], hx);
-            dy = min_image(dy, g.box[1], hy);
-            dz = min_image(dz, g.box[2], hz);
+    // indices are fetched one stage ahead, so that kRowU gathers are in flight while the
+    // previous kRowU pairs are evaluated
+    int jn[kRowU];
+#pragma unroll
+    for (int u = 0; u < kRowU; ++u) jn[u] = u < count ? row[(size_t)u * 32] : self;
+    for (int k0 = 0; k0 < count; k0 += kRowU) {
+        double bx[kRowU], by[kRowU], bz[kRowU], bm[kRowU];
+        int j[kRowU];
+#pragma unroll
+        for (int u = 0; u < kRowU; ++u) {
+            j[u] = jn[u];
+            load4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
         }
-        const double rsq = rsq_exact(dx, dy, dz);
-        const double rr = sqrt(rsq);
-        double hi = hinv, q = qn;
-        if (!UNIFORM_H) {
-            const int oj = perm[j];
-            const double h = h_orig[oj < orig ? oj : orig];       // properties.py:88: h of the first member
-            hi = 1.0 / h;
-            q = lucy_norm3(h);
+#pragma unroll
+        for (int u = 0; u < kRowU; ++u) {
+            const int kn = k0 + kRowU + u;
+            jn[u] = kn < count ? row[(size_t)kn * 32] : self;
         }
-        const double s = rr * hi;
-        if (s < 1.0) {                                            // spkernel.py:106
-            const double t = 1.0 - s;
-            acc += (q * (1.0 + 3.0 * s) * (t * t * t)) * bm;      // spkernel.py:107, properties.py:90-91
+#pragma unroll
+        for (int u = 0; u < kRowU; ++u) {
+            double dx = bx[u] - ax, dy = by[u] - ay, dz = bz[u] - az;
+            if (WRAP) {
+                dx = min_image(dx, g.box[0], hx);
+                dy = min_image(dy, g.box[1], hy);
+                dz = min_image(dz, g.box[2], hz);
+            }
+            const double rsq = rsq_exact(dx, dy, dz);
+            const double rr = sqrt(rsq);
+            double hi = hinv, q = qn;
+            if (!UNIFORM_H) {
+                const int oj = perm[j[u]];
+                const double h = h_orig[oj < orig ? oj : orig];   // properties.py:88: h of the first member
+                hi = 1.0 / h;
+                q = lucy_norm3(h);
+            }
+            const double s = rr * hi;
+            if (s < 1.0 && k0 + u < count) {                      // spkernel.py:106
+                const double t = 1.0 - s;
+                acc += (q * (1.0 + 3.0 * s) * (t * t * t)) * bm[u];   // spkernel.py:107, properties.py:90-91
+            }
         }
     }
     return acc;
@@ -502,8 +559,8 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
     const double hinv = 1.0 / h0, qn = lucy_norm3(h0);
     const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
     double sum;
-    if (skip) sum = density_row<UNIFORM_H, false>(g, pos4, perm, h_orig, row, count, orig, ax, ay, az, hinv, qn);
-    else sum = density_row<UNIFORM_H, true>(g, pos4, perm, h_orig, row, count, orig, ax, ay, az, hinv, qn);
+    if (skip) sum = density_row<UNIFORM_H, false>(g, pos4, perm, h_orig, row, count, orig, a, ax, ay, az, hinv, qn);
+    else sum = density_row<UNIFORM_H, true>(g, pos4, perm, h_orig, row, count, orig, a, ax, ay, az, hinv, qn);
     if (!active) return;
     // properties.py:76-77: every particle starts from W(0; h[0]) -- not m_i * W(0; h_i)
     const double rho = qn + sum;
@@ -533,53 +590,70 @@ pressure_term_kernel(int n, const int32_t *__restrict__ perm, const double *__re
 
 struct ForceAcc { double ax, ay, az, du; };
 
+constexpr int kRowUF = 2;            // force: 8 doubles per neighbour, so a shorter stage
+
 template <bool UNIFORM_H, bool WRAP>
 __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *__restrict__ pos4,
                                               const double *__restrict__ vel4,
                                               const int32_t *__restrict__ perm,
                                               const double *__restrict__ h_orig,
-                                              const int32_t *__restrict__ row, int count, int orig,
+                                              const int32_t *__restrict__ row, int count, int orig, int self,
                                               double px, double py, double pz, double vx, double vy,
                                               double vz, double Ai, double hinv, double c2,
                                               double fcutsq, bool two_d)
 {
     ForceAcc f = {0.0, 0.0, 0.0, 0.0};
     const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
-    for (int k = 0; k < count; ++k) {
-        const int j = row[(size_t)k * 32];
-        double bx, by, bz, bm, wx, wy, wz, Aj;
-        load4(pos4 + 4 * (size_t)j, bx, by, bz, bm);
-        load4(vel4 + 4 * (size_t)j, wx, wy, wz, Aj);
-        // Pair (i<j in original order) contributes +a to i and -a to j with dr = r_j - r_i.
-        // Seen from this particle: dr = r_other - r_self and the term enters with +.
-        double dx = bx - px, dy = by - py, dz = bz - pz;
-        if (WRAP) {
-            dx = min_image(dx, g.box[0], hx);
-            dy = min_image(dy, g.box[1], hy);
-            dz = min_image(dz, g.box[2], hz);
+    int jn[kRowUF];
+#pragma unroll
+    for (int u = 0; u < kRowUF; ++u) jn[u] = u < count ? row[(size_t)u * 32] : self;
+    for (int k0 = 0; k0 < count; k0 += kRowUF) {
+        double bx[kRowUF], by[kRowUF], bz[kRowUF], bm[kRowUF], wx[kRowUF], wy[kRowUF], wz[kRowUF], Aj[kRowUF];
+        int j[kRowUF];
+#pragma unroll
+        for (int u = 0; u < kRowUF; ++u) {
+            j[u] = jn[u];
+            load4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
+            load4(vel4 + 4 * (size_t)j[u], wx[u], wy[u], wz[u], Aj[u]);
         }
-        const double rsq = rsq_exact(dx, dy, dz);
-        const double rr = sqrt(rsq);
-        double hi = hinv, cc = c2;
-        if (!UNIFORM_H) {
-            const int oj = perm[j];
-            const double h = h_orig[oj < orig ? oj : orig];
-            hi = 1.0 / h;
-            cc = -12.0 * lucy_norm3(h) * hi * hi;
+#pragma unroll
+        for (int u = 0; u < kRowUF; ++u) {
+            const int kn = k0 + kRowUF + u;
+            jn[u] = kn < count ? row[(size_t)kn * 32] : self;
         }
-        const double s = rr * hi;
-        // forces.py:40 cutoff on rij^2; spkernel.py:106,109: zero outside h and at r == 0
-        if (s < 1.0 && rr * rr <= fcutsq) {
-            // q(-12 r^3/h^4 + 24 r^2/h^3 - 12 r/h^2)/r = -(12 q / h^2) (1 - r/h)^2   (spkernel.py:113-114)
-            const double t = 1.0 - s;
-            const double fac = (cc * (t * t)) * (Ai + Aj);          // ps * dW/dr / r  (forces.py:353-357)
-            const double gx = fac * dx, gy = fac * dy, gz = two_d ? 0.0 : fac * dz;
-            f.ax += gx;
-            f.ay += gy;
-            f.az += gz;
-            // du = 0.5 * a . dv with dv = v_j - v_i; symmetric in the pair (forces.py:366-368)
-            const double dot = gx * (wx - vx) + gy * (wy - vy) + gz * (wz - vz);
-            f.du += (0.5 * dot) * bm;
+#pragma unroll
+        for (int u = 0; u < kRowUF; ++u) {
+            // Pair (i<j in original order) contributes +a to i and -a to j with dr = r_j - r_i.
+            // Seen from this particle: dr = r_other - r_self and the term enters with +.
+            double dx = bx[u] - px, dy = by[u] - py, dz = bz[u] - pz;
+            if (WRAP) {
+                dx = min_image(dx, g.box[0], hx);
+                dy = min_image(dy, g.box[1], hy);
+                dz = min_image(dz, g.box[2], hz);
+            }
+            const double rsq = rsq_exact(dx, dy, dz);
+            const double rr = sqrt(rsq);
+            double hi = hinv, cc = c2;
+            if (!UNIFORM_H) {
+                const int oj = perm[j[u]];
+                const double h = h_orig[oj < orig ? oj : orig];
+                hi = 1.0 / h;
+                cc = -12.0 * lucy_norm3(h) * hi * hi;
+            }
+            const double s = rr * hi;
+            // forces.py:40 cutoff on rij^2; spkernel.py:106,109: zero outside h and at r == 0
+            if (s < 1.0 && rr * rr <= fcutsq && k0 + u < count) {
+                // q(-12 r^3/h^4 + 24 r^2/h^3 - 12 r/h^2)/r = -(12 q / h^2) (1 - r/h)^2   (spkernel.py:113-114)
+                const double t = 1.0 - s;
+                const double fac = (cc * (t * t)) * (Ai + Aj[u]);   // ps * dW/dr / r  (forces.py:353-357)
+                const double gx = fac * dx, gy = fac * dy, gz = two_d ? 0.0 : fac * dz;
+                f.ax += gx;
+                f.ay += gy;
+                f.az += gz;
+                // du = 0.5 * a . dv with dv = v_j - v_i; symmetric in the pair (forces.py:366-368)
+                const double dot = gx * (wx[u] - vx) + gy * (wy[u] - vy) + gz * (wz[u] - vz);
+                f.du += (0.5 * dot) * bm[u];
+            }
         }
     }
     return f;
@@ -612,8 +686,8 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
     const double hinv = 1.0 / h0, c2 = -12.0 * lucy_norm3(h0) * hinv * hinv;
     const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
     ForceAcc f;
-    if (skip) f = force_row<UNIFORM_H, false>(g, pos4, vel4, perm, h_orig, row, count, orig, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
-    else f = force_row<UNIFORM_H, true>(g, pos4, vel4, perm, h_orig, row, count, orig, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
+    if (skip) f = force_row<UNIFORM_H, false>(g, pos4, vel4, perm, h_orig, row, count, orig, a, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
+    else f = force_row<UNIFORM_H, true>(g, pos4, vel4, perm, h_orig, row, count, orig, a, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
     if (!active) return;
     (void)pm;
     // the reference accumulates into vdot/udot (particles.py:549-550 zeroes them per evaluation)
@@ -1006,15 +1080,21 @@ int sph_nlist_build(const sph_grid *g, const sph_buffers *b, void *stream)
     static bool configured = false;
     const size_t smem = sizeof(float4) * kNlWin * kNlWarps;
     if (!configured) {
-        cudaFuncSetAttribute(nlist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(nlist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(nlist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         configured = true;
     }
+    const bool small = g->ncl[0] < 3 || g->ncl[1] < 3 || g->ncl[2] < 3;
     const int64_t warps_needed = g->ncode;
     int64_t blocks = (warps_needed + kNlWarps - 1) / kNlWarps;
     const int64_t cap = (int64_t)sm_count() * 3 * 8;       // a few resident waves, grid-stride beyond
     if (blocks > cap) blocks = cap;
-    nlist_kernel<<<(unsigned)blocks, kNlWarps * 32, smem, (cudaStream_t)stream>>>(
-        *g, b->n, b->max_nbrs, b->cell_start, b->rel4, b->pos4, b->nbr, b->cnt, b->status);
+    if (small)
+        nlist_kernel<true><<<(unsigned)blocks, kNlWarps * 32, smem, (cudaStream_t)stream>>>(
+            *g, b->n, b->max_nbrs, b->cell_start, b->rel4, b->pos4, b->nbr, b->cnt, b->status);
+    else
+        nlist_kernel<false><<<(unsigned)blocks, kNlWarps * 32, smem, (cudaStream_t)stream>>>(
+            *g, b->n, b->max_nbrs, b->cell_start, b->rel4, b->pos4, b->nbr, b->cnt, b->status);
     return launch_status();
 }
 

@@ -73,6 +73,8 @@ class SphEvaluator(object):
         be = self.nl.backend
         st = be.status()
         if st.flags & _lib.SPH_F_NBR_OVERFLOW:
+            if int(st.max_count) <= be.K:
+                raise _lib.SphError("inconsistent neighbour overflow status")
             be.user_max_nbrs = None
             be.ensure(be.n, K=int(st.max_count) + max(4, int(st.max_count) // 8))
             self.evaluate()
