@@ -36,11 +36,17 @@ constexpr int kNlWin = 512;          // candidates staged per warp per window
 
 struct __align__(16) d2 { double x, y; };
 
+// One 256-bit load (LDG.E.ENL2.256) of a 32-byte-aligned row of four doubles: a gathered row
+// costs one L1 request instead of two 128-bit ones -- the L1 data pipe is what bounds the
+// density and force passes (profiles/r1a_kernels.txt).
 __device__ __forceinline__ void load4(const double *p, double &a, double &b, double &c, double &d)
 {
-    const double2 u = __ldg(reinterpret_cast<const double2 *>(p));
-    const double2 w = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-    a = u.x; b = u.y; c = w.x; d = w.y;
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+
+__device__ __forceinline__ void store4(double *p, double a, double b, double c, double d)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 
 __device__ __forceinline__ uint32_t pdep32(uint32_t v, uint32_t mask)
@@ -270,12 +276,8 @@ gather_kernel(const __grid_constant__ sph_grid g, int n, const int32_t *__restri
     const size_t i = (size_t)perm[a];
     const double x = r[3 * i], y = r[3 * i + 1], z = r[3 * i + 2];
     const CellLoc c = locate(g, x, y, z);
-    double2 *p = reinterpret_cast<double2 *>(pos4 + 4 * (size_t)a);
-    p[0] = make_double2(x, y);
-    p[1] = make_double2(z, m[i]);
-    double2 *q = reinterpret_cast<double2 *>(vel4 + 4 * (size_t)a);
-    q[0] = make_double2(v[3 * i], v[3 * i + 1]);
-    q[1] = make_double2(v[3 * i + 2], 0.0);
+    store4(pos4 + 4 * (size_t)a, x, y, z, m[i]);
+    store4(vel4 + 4 * (size_t)a, v[3 * i], v[3 * i + 1], v[3 * i + 2], 0.0);
     reinterpret_cast<float4 *>(rel4)[a] = make_float4(c.rx, c.ry, c.rz, __uint_as_float(c.code));
 }
 
