@@ -45,19 +45,25 @@ class NeighbourBackend(object):
         self.press_ready = False    # vel4[.,3] holds press/rho^2 of the last density pass
 
     # ------------------------------------------------------------------ planning / memory
-    def plan(self, box, cutoff, tolerance, n, r=None, slab=None):
+    def plan(self, box, cutoff, tolerance, n, r=None, slab=None, occ=None, n_hint=None):
         """Choose the cell grid.  Re-planned only when (box, cutoff, tolerance, n, slab) change;
-        the occupancy extents (one reduction + sync) only steer cell coarsening, never results."""
-        key = (tuple(float(b) for b in box), float(cutoff), float(tolerance), int(n), slab)
+        the occupancy extents (one reduction + sync, or `occ` = (lo, hi) given by the caller) only
+        steer cell coarsening, never results.  `n_hint` overrides n as the table-size budget (the
+        slab decomposition passes the global particle count so every rank plans the same grid)."""
+        key = (tuple(float(b) for b in box), float(cutoff), float(tolerance),
+               int(n) if n_hint is None else int(n_hint), slab)
         if key == self.grid_key:
             return
         lo = hi = None
-        if r is not None and n > 0:
+        if occ is not None:
+            lo, hi = box3(occ[0]), box3(occ[1])
+        elif r is not None and n > 0:
             ext = torch.stack([r[:n].amin(dim=0), r[:n].amax(dim=0)]).cpu()
             if bool(torch.isfinite(ext).all()):
                 lo = box3(ext[0].tolist())
                 hi = box3(ext[1].tolist())
-        check(self.lib.sph_grid_plan(box3(box), float(cutoff), float(tolerance), int(n), lo, hi,
+        check(self.lib.sph_grid_plan(box3(box), float(cutoff), float(tolerance),
+                                     int(n) if n_hint is None else int(n_hint), lo, hi,
                                      ctypes.byref(self.grid)), "sph_grid_plan")
         if slab is not None:
             check(self.lib.sph_grid_restrict_x(ctypes.byref(self.grid), int(slab[0]), int(slab[1])),

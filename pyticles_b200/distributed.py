@@ -1,0 +1,318 @@
+"""Multi-GPU slab decomposition of the SPH step.
+
+The reference is single process; this is the B200-native scaling of its hot path.  The periodic
+box is cut along x into slabs of whole cell layers, one process per GPU (torch.distributed:
+nccl on GPUs, gloo in the CPU tests).  Positions keep their GLOBAL coordinates everywhere, so the
+reference's minimum image and pair predicate apply unchanged on every rank.
+
+Per derivative evaluation
+    A  ghost exchange: the two boundary cell layers of each slab (r, v, m, h, t, global id) go to the
+       x-neighbours (ring, periodic)                                     -> all_to_all_single
+    1  cell list + neighbour pass + density/EOS over owned + ghost particles (local grid =
+       owned layers + one ghost layer each side, sph_grid_restrict_x)
+    B  ghost exchange of (p, rho) for the same particles, same order     -> all_to_all_single
+    2  force pass; results of owned particles are kept
+After integration `migrate()` re-homes particles whose cell layer changed owner.  There is no
+other collective on the data path.  A pair is reported by the rank that owns its lower-global-id
+member, so the union of the per-rank pair lists is the global i<j set exactly once.
+
+`SlabDecomposition` is pure torch + torch.distributed (device agnostic: it is what the gloo tests
+exercise on CPU); `SlabSphEvaluator` adds the CUDA passes.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+NCOL = 10          # r(3) v(3) m h t gid
+C_R, C_V, C_M, C_H, C_T, C_GID = 0, 3, 6, 7, 8, 9
+
+
+class SlabDecomposition(object):
+    def __init__(self, box, cutoff, tolerance, n_total, occ=None, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.box = tuple(float(b) for b in box)
+        self.cutoff, self.tolerance, self.n_total = float(cutoff), float(tolerance), int(n_total)
+        self.occ = occ
+        g = _lib.SphGrid()
+        lo = _lib.box3(occ[0]) if occ is not None else None
+        hi = _lib.box3(occ[1]) if occ is not None else None
+        _lib.check(_lib.load().sph_grid_plan(_lib.box3(self.box), self.cutoff, self.tolerance, self.n_total,
+                                             lo, hi, ctypes.byref(g)), "sph_grid_plan")
+        self.nc = int(g.nc[0])
+        self.inv_w = float(g.inv_w[0])
+        W = self.world
+        if W > 1 and self.nc < 2 * W + 1:
+            raise _lib.SphError("box has %d cell layers along x: too few for %d slabs" % (self.nc, W))
+        self.bounds = [(k * self.nc) // W for k in range(W + 1)]
+        self.lay0, self.lay1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+        # local grid: one ghost layer on each side of the owned layers
+        self.slab = ((self.lay0 - 1) % self.nc, (self.lay1 - self.lay0) + 2) if W > 1 else None
+        self.left, self.right = (self.rank - 1) % W, (self.rank + 1) % W
+        self._halo = None
+
+    # ------------------------------------------------------------------ geometry
+    def layer_of(self, x):
+        """Global x cell layer, with the kernel's own formula (floor(x * inv_w) mod nc)."""
+        return torch.floor(x * self.inv_w).to(torch.int64) % self.nc
+
+    def owner_of_layer(self, layer):
+        b = torch.tensor(self.bounds[1:], dtype=torch.int64, device=layer.device)
+        return torch.searchsorted(b, layer, right=True)
+
+    # ------------------------------------------------------------------ exchange primitive
+    def _exchange(self, rows, dest, splits=None):
+        """Send row k to rank dest[k]; returns (received rows, send order, send splits, recv splits)."""
+        W = self.world
+        if splits is None:
+            order = torch.argsort(dest, stable=True)
+            counts = torch.bincount(dest, minlength=W)
+            rc = torch.empty_like(counts)
+            dist.all_to_all_single(rc, counts, group=self.group)
+            send_splits, recv_splits = counts.tolist(), rc.tolist()
+        else:
+            order, send_splits, recv_splits = splits
+        send = rows[order].contiguous()
+        recv = torch.empty((sum(recv_splits), rows.shape[1]), dtype=rows.dtype, device=rows.device)
+        dist.all_to_all_single(recv, send, output_split_sizes=recv_splits, input_split_sizes=send_splits,
+                               group=self.group)
+        return recv, (order, send_splits, recv_splits)
+
+    def migrate(self, own):
+        """Re-home rows (n, NCOL) whose cell layer belongs to another rank."""
+        if self.world == 1:
+            return own
+        dest = self.owner_of_layer(self.layer_of(own[:, C_R]))
+        recv, _ = self._exchange(own, dest)
+        return recv
+
+    def halo_select(self, own):
+        """Indices (into own) and destinations of the boundary-layer particles."""
+        layer = self.layer_of(own[:, C_R])
+        li = torch.nonzero(layer == self.lay0).flatten()
+        ri = torch.nonzero(layer == self.lay1 - 1).flatten()
+        idx = torch.cat([li, ri])
+        dest = torch.cat([torch.full_like(li, self.left), torch.full_like(ri, self.right)])
+        return idx, dest
+
+    def halo_exchange(self, own):
+        """Exchange A: returns the ghost rows; remembers the pattern for halo_exchange_again."""
+        if self.world == 1:
+            self._halo = None
+            return own[:0]
+        idx, dest = self.halo_select(own)
+        ghosts, pattern = self._exchange(own[idx], dest)
+        self._halo = (idx, pattern)
+        return ghosts
+
+    def halo_exchange_again(self, cols):
+        """Exchange B: per-particle columns (n_own, C) of the same ghosts, in the same order."""
+        if self.world == 1:
+            return cols[:0]
+        idx, pattern = self._halo
+        out, _ = self._exchange(cols[idx], None, splits=pattern)
+        return out
+
+    def owns_pair(self, gid_i, gid_j, owned_i, owned_j):
+        """A pair belongs to the rank that owns its lower-global-id member."""
+        return torch.where(gid_i < gid_j, owned_i, owned_j)
+
+
+class SlabSphEvaluator(object):
+    """bench.py / long-run driver: one rank's share of the distributed derivative evaluation."""
+    kernel_names = {"cells+reorder": "bin_kernel+scan+scatter_kernel+cell_sort_kernel+gather_kernel",
+                    "neighbour": "nlist_kernel", "density": "density_kernel<true>", "force": "force_kernel<true>",
+                    "halo": "all_to_all_single (NCCL)"}
+    ncu_traffic = {}
+
+    def __init__(self, own, box, cutoff, tol, fcut, eos, n_total, device, occ=None):
+        from .backend import NeighbourBackend
+        self.dec = SlabDecomposition(box, cutoff, tol, n_total, occ=occ)
+        self.device = torch.device(device)
+        self.box, self.cutoff, self.tol, self.fcut, self.eos = box, cutoff, tol, fcut, eos
+        self.own = self.dec.migrate(own)
+        self.n_owned = int(self.own.shape[0])
+        cnt = torch.tensor([self.n_owned], dtype=torch.int64, device=self.device)
+        if self.dec.world > 1:
+            dist.all_reduce(cnt)
+        self.n_total = int(cnt.item())
+        self.be = NeighbourBackend(self.device)
+        vol = box[0] * box[1] * box[2]
+        rl = (cutoff * cutoff + tol * tol) ** 0.5
+        self.be.user_max_nbrs = int(1.6 * 4.18879 * rl ** 3 * self.n_total / vol) + 24
+        self.launches_per_eval = 12
+        self._events = []
+        self.loc = {}
+
+    @property
+    def max_nbrs(self):
+        return self.be.K
+
+    def _local(self, name, n, cols=None):
+        shape = (n,) if cols is None else (n, cols)
+        t = self.loc.get(name)
+        if t is None or t.shape[0] < n:
+            cap = int(n * 1.05) + 1024
+            t = torch.zeros((cap,) if cols is None else (cap, cols), dtype=torch.float64, device=self.device)
+            self.loc[name] = t
+        return t[:n]
+
+    def evaluate(self, timed=False):
+        dec, be = self.dec, self.be
+        ev = None
+        if timed:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+            ev[0].record()
+        own = self.own
+        ghosts = dec.halo_exchange(own)                       # A
+        no, ng = own.shape[0], ghosts.shape[0]
+        n = no + ng
+        r, v = self._local("r", n, 3), self._local("v", n, 3)
+        m, h, t = self._local("m", n), self._local("h", n), self._local("t", n)
+        for dst, col, w in ((r, C_R, 3), (v, C_V, 3)):
+            dst[:no] = own[:, col:col + w]
+            dst[no:] = ghosts[:, col:col + w]
+        for dst, col in ((m, C_M), (h, C_H), (t, C_T)):
+            dst[:no] = own[:, col]
+            dst[no:] = ghosts[:, col]
+        rho, p, pco, u = (self._local(k, n) for k in ("rho", "p", "pco", "u"))
+        vdot, udot = self._local("vdot", n, 3), self._local("udot", n)
+        if timed:
+            ev[1].record()
+        be.plan(self.box, self.cutoff, self.tol, n, slab=dec.slab, occ=dec.occ, n_hint=dec.n_total)
+        if be.n != n or not be.K:
+            be.ensure(n, K=be.K or None)
+        be.cells_and_gather(r, v, m)
+        if timed:
+            ev[2].record()
+        be.nlist()
+        if timed:
+            ev[3].record()
+        vdot.zero_()
+        udot.zero_()
+        be.density_eos(self.eos, h, True, rho, p, pco, u, t)
+        if timed:
+            ev[4].record()
+        if ng:
+            pr = dec.halo_exchange_again(torch.stack([p[:no], rho[:no]], dim=1))     # B
+            p[no:] = pr[:, 0]
+            rho[no:] = pr[:, 1]
+        if timed:
+            ev[5].record()
+        be.force(p, rho, h, True, self.fcut, 3, vdot, udot, reuse_press=(ng == 0))
+        if timed:
+            ev[6].record()
+            self._events.append(ev)
+        self.n_local = n
+        self.result = dict(rho=rho[:no], p=p[:no], pco=pco[:no], u=u[:no], vdot=vdot[:no], udot=udot[:no])
+
+    def check(self):
+        torch.cuda.synchronize()
+        st = self.be.status()
+        if st.flags & _lib.SPH_F_NBR_OVERFLOW:
+            if int(st.max_count) <= self.be.K:
+                raise _lib.SphError("inconsistent neighbour overflow status")
+            self.be.user_max_nbrs = None
+            self.be.ensure(self.be.n, K=int(st.max_count) + max(4, int(st.max_count) // 8))
+            self.evaluate()
+            return self.check()
+        if st.flags & _lib.SPH_F_OUT_OF_SLAB:
+            raise _lib.SphError("a particle lies outside this rank's cell layers (missing migrate()?)")
+        return st
+
+    def reset_pass_timers(self):
+        self._events = []
+
+    def pass_times(self):
+        names = ["halo", "cells+reorder", "neighbour", "density", "halo_b", "force"]
+        tot = dict.fromkeys(names, 0.0)
+        for ev in self._events:
+            for k, nm in enumerate(names):
+                tot[nm] += ev[k].elapsed_time(ev[k + 1])
+        k = max(1, len(self._events))
+        out = {nm: tot[nm] / k for nm in names}
+        out["halo"] += out.pop("halo_b")
+        return out
+
+    def pairs_per_particle(self):
+        return self.be.count_links() / 2.0 / max(1, self.n_local)
+
+    def local_pairs_global_ids(self):
+        """(gid_i, gid_j) of the pairs this rank reports (lower-gid member owned here), sorted."""
+        no = self.n_owned
+        gid = torch.cat([self.own[:, C_GID], self.dec.halo_exchange(self.own)[:, C_GID]]).to(torch.int64)
+        iap = self.be.export_pairs().to(torch.int64)
+        gi, gj = gid[iap[:, 0]], gid[iap[:, 1]]
+        keep = self.dec.owns_pair(gi, gj, iap[:, 0] < no, iap[:, 1] < no)
+        lo, hi = torch.minimum(gi, gj)[keep], torch.maximum(gi, gj)[keep]
+        key = lo * (self.n_total + 1) + hi
+        order = torch.argsort(key)
+        return torch.stack([lo[order], hi[order]], dim=1)
+
+    def run_e2e(self, steps, warmup):
+        own = self.own
+        h_in = torch.empty(own.shape, dtype=own.dtype, pin_memory=True).copy_(own)
+        outs = None
+        h2d = own.numel() * own.element_size()
+
+        def one():
+            nonlocal outs
+            self.own.copy_(h_in, non_blocking=True)
+            self.evaluate()
+            res = [self.result[k] for k in ("rho", "p", "vdot", "udot")]
+            if outs is None:
+                outs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in res]
+            for d, hh in zip(res, outs):
+                hh.copy_(d, non_blocking=True)
+
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        d2h = sum(t.numel() * t.element_size() for t in outs)
+        tot = torch.tensor([h2d, d2h], dtype=torch.int64, device=self.device)
+        dist.all_reduce(tot)
+        return {"ms": e0.elapsed_time(e1), "steps": steps, "h2d": int(tot[0]), "d2h": int(tot[1])}
+
+
+def make_rows(r, v, m, h, t, gid):
+    n = r.shape[0]
+    rows = torch.empty((n, NCOL), dtype=torch.float64, device=r.device)
+    rows[:, C_R:C_R + 3] = r
+    rows[:, C_V:C_V + 3] = v
+    rows[:, C_M], rows[:, C_H], rows[:, C_T] = m, h, t
+    rows[:, C_GID] = gid.to(torch.float64)
+    return rows
+
+
+def make_bench_system(wl, world, rank, device, seed, h, cutoff, tol, fcut, eos):
+    """This rank's share of bench.py's lattice-plus-jitter box (weak: the box grows along x with
+    the number of ranks; strong: the fixed box is cut along x)."""
+    import bench
+    nx, ny, nz = wl["dims"]
+    if wl["scaling"] == "strong":
+        if nx % world:
+            raise _lib.SphError("strong-scaled workload needs nx divisible by the number of GPUs")
+        nxl, nx_tot = nx // world, nx
+    else:
+        nxl, nx_tot = nx, nx * world
+    box = (float(nx_tot), float(ny), float(wl["zbox"] or nz))
+    n = nxl * ny * nz
+    r, v = bench.lattice_on_device((nxl, ny, nz), rank * nxl, device, seed + rank)
+    gid = torch.arange(n, device=device, dtype=torch.int64) + rank * n
+    one = torch.ones(n, dtype=torch.float64, device=device)
+    rows = make_rows(r, v, one, one * h, one, gid)
+    del r, v, one, gid
+    occ = ((0.0, 0.0, 0.0), (box[0], box[1], float(nz))) if wl["zbox"] else None
+    return SlabSphEvaluator(rows, box, cutoff, tol, fcut, eos, n * world, device, occ=occ)
