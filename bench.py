@@ -243,8 +243,6 @@ def main():
         sim.evaluate()
     sim.check()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -253,6 +251,9 @@ def main():
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()                 # all ranks enter the timed region together
+        torch.cuda.synchronize()
     t0 = time.time()
     e0.record()
     for _ in range(args.steps):

@@ -195,6 +195,18 @@ int sph_compress(const sph_grid *grid, const sph_buffers *buf, void *stream);
 int sph_ponder_rebuild(const double *d_r_old, const double *d_r, int32_t n, double tol_sq,
                        sph_status *d_status, void *stream);
 
+/* ------------------------------------------------------------------ multi-GPU slab decomposition */
+
+/* Indices of the particles whose global x cell layer (floor(x * inv_w) mod nc, the binning
+ * formula of sph_cells_build) is layer_left / layer_right: the two boundary layers of a slab,
+ * i.e. the ghosts its x-neighbours need.  x is read with a stride (in doubles).  d_counts[0..1]
+ * receive the two counts (they may exceed `cap`, the capacity of each index list: only the
+ * first cap indices are stored, so the caller retries with larger lists); index order inside
+ * each list is unspecified (sort for determinism). */
+int sph_slab_select(const double *d_x, int64_t stride, int32_t n, double inv_w, int32_t nc,
+                    int32_t layer_left, int32_t layer_right, int32_t *d_idx_left, int32_t *d_idx_right,
+                    int32_t cap, uint32_t *d_counts, void *stream);
+
 /* ------------------------------------------------------------------ stepping helpers ("next" rows) */
 
 /* x <- a + s * b over len doubles: the state-vector updates of integrator.py:37-41,44-59,62-95. */

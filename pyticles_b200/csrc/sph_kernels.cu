@@ -885,6 +885,36 @@ box_kernel(double Lx, double Ly, double Lz, int kind, double *__restrict__ r, do
     }
 }
 
+// Slab decomposition: indices of the particles in the two boundary cell layers of this rank's slab.
+__global__ void __launch_bounds__(kBlock)
+slab_select_kernel(const double *__restrict__ x, int64_t stride, int n, double inv_w, int nc, int lay_left,
+                   int lay_right, int32_t *__restrict__ idx_left, int32_t *__restrict__ idx_right,
+                   uint32_t cap, uint32_t *__restrict__ counts)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool l = false, r = false;
+    if (i < n) {
+        double f = floor(x[(size_t)i * stride] * inv_w);            // bin_kernel's own formula
+        if (!(fabs(f) < 4.0e15)) f = 0.0;
+        long long c = (long long)f % nc;
+        if (c < 0) c += nc;
+        l = (int)c == lay_left;
+        r = (int)c == lay_right;
+    }
+    const uint32_t ml = __ballot_sync(0xffffffffu, l), mr = __ballot_sync(0xffffffffu, r);
+    const int lane = threadIdx.x & 31;
+    uint32_t bl = 0, br = 0;
+    if (lane == 0) {
+        if (ml) bl = atomicAdd(counts, (uint32_t)__popc(ml));
+        if (mr) br = atomicAdd(counts + 1, (uint32_t)__popc(mr));
+    }
+    bl = __shfl_sync(0xffffffffu, bl, 0);
+    br = __shfl_sync(0xffffffffu, br, 0);
+    const uint32_t lt = (1u << lane) - 1u;
+    if (l && bl + __popc(ml & lt) < cap) idx_left[bl + __popc(ml & lt)] = i;
+    if (r && br + __popc(mr & lt) < cap) idx_right[br + __popc(mr & lt)] = i;
+}
+
 inline int blocks_for(int64_t n, int per) { return (int)((n + per - 1) / per); }
 
 inline int launch_status()
@@ -1198,6 +1228,19 @@ int sph_ponder_rebuild(const double *d_r_old, const double *d_r, int32_t n, doub
     cudaMemsetAsync(&d_status->dsq_max_bits, 0, sizeof(unsigned long long), s);
     if (n > 0) ponder_kernel<<<blocks_for(n, kBlock), kBlock, 0, s>>>(d_r_old, d_r, n, d_status);
     ponder_decide_kernel<<<1, 1, 0, s>>>(d_status, tol_sq);
+    return launch_status();
+}
+
+int sph_slab_select(const double *d_x, int64_t stride, int32_t n, double inv_w, int32_t nc,
+                    int32_t layer_left, int32_t layer_right, int32_t *d_idx_left, int32_t *d_idx_right,
+                    int32_t cap, uint32_t *d_counts, void *stream)
+{
+    if (n < 0 || nc <= 0 || cap < 0 || !d_counts || (n > 0 && (!d_x || !d_idx_left || !d_idx_right))) return SPH_E_BADARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(d_counts, 0, 2 * sizeof(uint32_t), s);
+    if (n > 0)
+        slab_select_kernel<<<blocks_for(n, kBlock), kBlock, 0, s>>>(d_x, stride, n, inv_w, nc, layer_left,
+                                                                    layer_right, d_idx_left, d_idx_right, (uint32_t)cap, d_counts);
     return launch_status();
 }
 

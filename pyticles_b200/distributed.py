@@ -92,9 +92,35 @@ class SlabDecomposition(object):
 
     def halo_select(self, own):
         """Indices (into own) and destinations of the boundary-layer particles."""
-        layer = self.layer_of(own[:, C_R])
-        li = torch.nonzero(layer == self.lay0).flatten()
-        ri = torch.nonzero(layer == self.lay1 - 1).flatten()
+        return self.halo_select_x(own[:, C_R])
+
+    def halo_select_x(self, x):
+        """Same, from the (possibly strided) x-coordinate column.  On CUDA the selection is one
+        pass of sph_slab_select; on CPU (gloo tests) it is plain torch."""
+        if x.is_cuda:
+            n = x.shape[0]
+            while True:
+                buf = getattr(self, "_sel_buf", None)
+                if buf is None or buf.device != x.device:
+                    cap = max(4096, int(4.0 * n / max(1, self.lay1 - self.lay0)))
+                    buf = self._sel_buf = torch.empty((2, cap), dtype=torch.int32, device=x.device)
+                    self._sel_cnt = torch.zeros(2, dtype=torch.int32, device=x.device)
+                cap = buf.shape[1]
+                _lib.check(_lib.load().sph_slab_select(
+                    ctypes.c_void_p(x.data_ptr()), int(x.stride(0)), int(n), self.inv_w, self.nc, int(self.lay0),
+                    int(self.lay1 - 1), ctypes.c_void_p(buf[0].data_ptr()), ctypes.c_void_p(buf[1].data_ptr()),
+                    int(cap), ctypes.c_void_p(self._sel_cnt.data_ptr()),
+                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "sph_slab_select")
+                nl, nr = (int(c) for c in self._sel_cnt.tolist())
+                if max(nl, nr) <= cap:
+                    break
+                self._sel_buf = torch.empty((2, 2 * max(nl, nr)), dtype=torch.int32, device=x.device)
+            li = torch.sort(buf[0, :nl]).values.to(torch.int64)
+            ri = torch.sort(buf[1, :nr]).values.to(torch.int64)
+        else:
+            layer = self.layer_of(x)
+            li = torch.nonzero(layer == self.lay0).flatten()
+            ri = torch.nonzero(layer == self.lay1 - 1).flatten()
         idx = torch.cat([li, ri])
         dest = torch.cat([torch.full_like(li, self.left), torch.full_like(ri, self.right)])
         return idx, dest
@@ -123,19 +149,24 @@ class SlabDecomposition(object):
 
 
 class SlabSphEvaluator(object):
-    """bench.py / long-run driver: one rank's share of the distributed derivative evaluation."""
+    """bench.py / long-run driver: one rank's share of the distributed derivative evaluation.
+    Owned particles live at the front of persistent structure-of-arrays tensors; the ghosts of
+    the current evaluation are appended behind them."""
     kernel_names = {"cells+reorder": "bin_kernel+scan+scatter_kernel+cell_sort_kernel+gather_kernel",
                     "neighbour": "nlist_kernel", "density": "density_kernel<true>", "force": "force_kernel<true>",
-                    "halo": "all_to_all_single (NCCL)"}
+                    "halo": "slab_select_kernel + all_to_all_single (NCCL)"}
     ncu_traffic = {}
+    IN = ("r", "v", "m", "h", "t")
+    OUT = ("rho", "p", "pco", "u", "vdot", "udot")
 
     def __init__(self, own, box, cutoff, tol, fcut, eos, n_total, device, occ=None):
         from .backend import NeighbourBackend
         self.dec = SlabDecomposition(box, cutoff, tol, n_total, occ=occ)
         self.device = torch.device(device)
         self.box, self.cutoff, self.tol, self.fcut, self.eos = box, cutoff, tol, fcut, eos
-        self.own = self.dec.migrate(own)
-        self.n_owned = int(self.own.shape[0])
+        self.S = {}
+        self.cap = 0
+        self._load_rows(self.dec.migrate(own))
         cnt = torch.tensor([self.n_owned], dtype=torch.int64, device=self.device)
         if self.dec.world > 1:
             dist.all_reduce(cnt)
@@ -146,20 +177,70 @@ class SlabSphEvaluator(object):
         self.be.user_max_nbrs = int(1.6 * 4.18879 * rl ** 3 * self.n_total / vol) + 24
         self.launches_per_eval = 12
         self._events = []
-        self.loc = {}
+        self.n_local = self.n_owned
+
+    # ------------------------------------------------------------------ storage
+    def _reserve(self, cap):
+        if cap <= self.cap:
+            return
+        cap = int(cap * 1.06) + 4096
+        shapes = dict(r=(cap, 3), v=(cap, 3), m=(cap,), h=(cap,), t=(cap,), gid=(cap,), rho=(cap,), p=(cap,),
+                      pco=(cap,), u=(cap,), vdot=(cap, 3), udot=(cap,))
+        for k, shp in shapes.items():
+            new = torch.zeros(shp, dtype=torch.int64 if k == "gid" else torch.float64, device=self.device)
+            old = self.S.get(k)
+            if old is not None:
+                new[:old.shape[0]] = old
+            self.S[k] = new
+        self.cap = cap
+
+    def _load_rows(self, rows):
+        n = rows.shape[0]
+        self.cap = 0
+        self.S = {}
+        self._reserve(n)
+        S = self.S
+        S["r"][:n], S["v"][:n] = rows[:, C_R:C_R + 3], rows[:, C_V:C_V + 3]
+        S["m"][:n], S["h"][:n], S["t"][:n] = rows[:, C_M], rows[:, C_H], rows[:, C_T]
+        S["gid"][:n] = rows[:, C_GID].to(torch.int64)
+        self.n_owned = int(n)
+
+    def _pack(self, idx):
+        S = self.S
+        return make_rows(S["r"][idx], S["v"][idx], S["m"][idx], S["h"][idx], S["t"][idx], S["gid"][idx])
+
+    def rows(self):
+        """Owned particles as (n, NCOL) rows (for migrate / checkpoints)."""
+        return self._pack(torch.arange(self.n_owned, device=self.device))
+
+    def migrate(self):
+        """Re-home owned particles whose cell layer changed owner (call after integration)."""
+        self._load_rows(self.dec.migrate(self.rows()))
+
+    @property
+    def own_gid(self):
+        return self.S["gid"][:self.n_owned]
 
     @property
     def max_nbrs(self):
         return self.be.K
 
-    def _local(self, name, n, cols=None):
-        shape = (n,) if cols is None else (n, cols)
-        t = self.loc.get(name)
-        if t is None or t.shape[0] < n:
-            cap = int(n * 1.05) + 1024
-            t = torch.zeros((cap,) if cols is None else (cap, cols), dtype=torch.float64, device=self.device)
-            self.loc[name] = t
-        return t[:n]
+    # ------------------------------------------------------------------ one evaluation
+    def _halo_a(self):
+        dec, S, no = self.dec, self.S, self.n_owned
+        if dec.world == 1:
+            dec._halo = None
+            return 0
+        idx, dest = dec.halo_select_x(S["r"][:no, 0])
+        ghosts, pattern = dec._exchange(self._pack(idx), dest)
+        dec._halo = (idx, pattern)
+        ng = int(ghosts.shape[0])
+        self._reserve(no + ng)
+        S = self.S
+        S["r"][no:no + ng], S["v"][no:no + ng] = ghosts[:, C_R:C_R + 3], ghosts[:, C_V:C_V + 3]
+        S["m"][no:no + ng], S["h"][no:no + ng], S["t"][no:no + ng] = ghosts[:, C_M], ghosts[:, C_H], ghosts[:, C_T]
+        S["gid"][no:no + ng] = ghosts[:, C_GID].to(torch.int64)
+        return ng
 
     def evaluate(self, timed=False):
         dec, be = self.dec, self.be
@@ -167,20 +248,11 @@ class SlabSphEvaluator(object):
         if timed:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
             ev[0].record()
-        own = self.own
-        ghosts = dec.halo_exchange(own)                       # A
-        no, ng = own.shape[0], ghosts.shape[0]
+        ng = self._halo_a()                                   # A
+        S, no = self.S, self.n_owned
         n = no + ng
-        r, v = self._local("r", n, 3), self._local("v", n, 3)
-        m, h, t = self._local("m", n), self._local("h", n), self._local("t", n)
-        for dst, col, w in ((r, C_R, 3), (v, C_V, 3)):
-            dst[:no] = own[:, col:col + w]
-            dst[no:] = ghosts[:, col:col + w]
-        for dst, col in ((m, C_M), (h, C_H), (t, C_T)):
-            dst[:no] = own[:, col]
-            dst[no:] = ghosts[:, col]
-        rho, p, pco, u = (self._local(k, n) for k in ("rho", "p", "pco", "u"))
-        vdot, udot = self._local("vdot", n, 3), self._local("udot", n)
+        r, v, m, h, t = (S[k][:n] for k in self.IN)
+        rho, p, pco, u, vdot, udot = (S[k][:n] for k in self.OUT)
         if timed:
             ev[1].record()
         be.plan(self.box, self.cutoff, self.tol, n, slab=dec.slab, occ=dec.occ, n_hint=dec.n_total)
@@ -242,9 +314,10 @@ class SlabSphEvaluator(object):
         return self.be.count_links() / 2.0 / max(1, self.n_local)
 
     def local_pairs_global_ids(self):
-        """(gid_i, gid_j) of the pairs this rank reports (lower-gid member owned here), sorted."""
+        """(gid_i, gid_j) of the pairs this rank reports (lower-gid member owned here), sorted.
+        Call after evaluate()."""
         no = self.n_owned
-        gid = torch.cat([self.own[:, C_GID], self.dec.halo_exchange(self.own)[:, C_GID]]).to(torch.int64)
+        gid = self.S["gid"][:self.n_local]
         iap = self.be.export_pairs().to(torch.int64)
         gi, gj = gid[iap[:, 0]], gid[iap[:, 1]]
         keep = self.dec.owns_pair(gi, gj, iap[:, 0] < no, iap[:, 1] < no)
@@ -254,25 +327,28 @@ class SlabSphEvaluator(object):
         return torch.stack([lo[order], hi[order]], dim=1)
 
     def run_e2e(self, steps, warmup):
-        own = self.own
-        h_in = torch.empty(own.shape, dtype=own.dtype, pin_memory=True).copy_(own)
-        outs = None
-        h2d = own.numel() * own.element_size()
+        """Every step: pinned-host r, v, m, h, t of the owned particles -> device; evaluate;
+        rho, p, vdot, udot -> pinned host."""
+        no = self.n_owned
+        ins = [self.S[k][:no] for k in self.IN]
+        h_in = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in ins]
+        outs = [self.S[k][:no] for k in ("rho", "p", "vdot", "udot")]
+        h_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
+        h2d = sum(t.numel() * t.element_size() for t in ins)
+        d2h = sum(t.numel() * t.element_size() for t in outs)
 
         def one():
-            nonlocal outs
-            self.own.copy_(h_in, non_blocking=True)
+            for d, hh in zip(ins, h_in):
+                d.copy_(hh, non_blocking=True)
             self.evaluate()
-            res = [self.result[k] for k in ("rho", "p", "vdot", "udot")]
-            if outs is None:
-                outs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in res]
-            for d, hh in zip(res, outs):
+            for d, hh in zip(outs, h_out):
                 hh.copy_(d, non_blocking=True)
 
         for _ in range(warmup):
             one()
         torch.cuda.synchronize()
         dist.barrier()
+        torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -280,7 +356,6 @@ class SlabSphEvaluator(object):
             one()
         e1.record()
         torch.cuda.synchronize()
-        d2h = sum(t.numel() * t.element_size() for t in outs)
         tot = torch.tensor([h2d, d2h], dtype=torch.int64, device=self.device)
         dist.all_reduce(tot)
         return {"ms": e0.elapsed_time(e1), "steps": steps, "h2d": int(tot[0]), "d2h": int(tot[1])}

@@ -43,7 +43,7 @@ def _worker(rank, world, port, q):
         ev = D.SlabSphEvaluator(rows, box, CUTOFF, TOL, FCUT, (2.0, 0.5, 1.0), n, dev)
         ev.evaluate()
         ev.check()
-        res = {"gid": ev.own[:, D.C_GID].to(torch.int64).cpu().numpy(),
+        res = {"gid": ev.own_gid.cpu().numpy(),
                "pairs": ev.local_pairs_global_ids().cpu().numpy()}
         for kx in ("rho", "p", "vdot", "udot"):
             res[kx] = ev.result[kx].cpu().numpy()
