@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "pyticles_b200.h"
 
@@ -484,8 +485,9 @@ template <bool UNIFORM_H, bool WRAP>
 __device__ __forceinline__ double density_row(const sph_grid &g, const double *__restrict__ pos4,
                                               const int32_t *__restrict__ perm,
                                               const double *__restrict__ h_orig,
-                                              const int32_t *__restrict__ row, int count, int orig, int self,
-                                              double ax, double ay, double az, double hinv, double qn)
+                                              const int32_t *__restrict__ row, size_t stride, int count,
+                                              int orig, int self, double ax, double ay, double az, double hinv,
+                                              double qn)
 {
     double acc = 0.0;
     const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
@@ -493,7 +495,7 @@ __device__ __forceinline__ double density_row(const sph_grid &g, const double *_
     // previous kRowU pairs are evaluated
     int jn[kRowU];
 #pragma unroll
-    for (int u = 0; u < kRowU; ++u) jn[u] = u < count ? row[(size_t)u * 32] : self;
+    for (int u = 0; u < kRowU; ++u) jn[u] = u < count ? row[(size_t)u * stride] : self;
     for (int k0 = 0; k0 < count; k0 += kRowU) {
         double bx[kRowU], by[kRowU], bz[kRowU], bm[kRowU];
         int j[kRowU];
@@ -505,7 +507,7 @@ __device__ __forceinline__ double density_row(const sph_grid &g, const double *_
 #pragma unroll
         for (int u = 0; u < kRowU; ++u) {
             const int kn = k0 + kRowU + u;
-            jn[u] = kn < count ? row[(size_t)kn * 32] : self;
+            jn[u] = kn < count ? row[(size_t)kn * stride] : self;
         }
 #pragma unroll
         for (int u = 0; u < kRowU; ++u) {
@@ -534,7 +536,11 @@ __device__ __forceinline__ double density_row(const sph_grid &g, const double *_
     return acc;
 }
 
-template <bool UNIFORM_H>
+// LPP lanes cooperate on one particle: lane q of the group takes neighbours q, q+LPP, ... of the
+// row, so that the lanes of a group gather consecutive rows (neighbours from one cell are
+// contiguous in the sorted arrays) and the per-lane trip counts even out; the partial sums are
+// combined with shuffles.
+template <bool UNIFORM_H, int LPP>
 __global__ void __launch_bounds__(kBlock)
 density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__restrict__ pos4,
                double *__restrict__ vel4, const float *__restrict__ rel4,
@@ -544,7 +550,8 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
                double *__restrict__ rho_out, double *__restrict__ p_out, double *__restrict__ pco_out,
                double *__restrict__ u_out, double *__restrict__ t_io)
 {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = gt / LPP, q = gt % LPP;
     const bool active = a < n;
     double ax = 0, ay = 0, az = 0, am = 0;
     int count = 0, orig = 0;
@@ -559,11 +566,14 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
     const bool skip = __all_sync(0xffffffffu, interior) && can_skip;
     const double h0 = h_orig[0];
     const double hinv = 1.0 / h0, qn = lucy_norm3(h0);
-    const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
+    const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K + q) * 32 + (a & 31);
+    const int mine = count > q ? (count - q + LPP - 1) / LPP : 0;
     double sum;
-    if (skip) sum = density_row<UNIFORM_H, false>(g, pos4, perm, h_orig, row, count, orig, a, ax, ay, az, hinv, qn);
-    else sum = density_row<UNIFORM_H, true>(g, pos4, perm, h_orig, row, count, orig, a, ax, ay, az, hinv, qn);
-    if (!active) return;
+    if (skip) sum = density_row<UNIFORM_H, false>(g, pos4, perm, h_orig, row, (size_t)32 * LPP, mine, orig, a, ax, ay, az, hinv, qn);
+    else sum = density_row<UNIFORM_H, true>(g, pos4, perm, h_orig, row, (size_t)32 * LPP, mine, orig, a, ax, ay, az, hinv, qn);
+#pragma unroll
+    for (int o = 1; o < LPP; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (!active || q != 0) return;
     // properties.py:76-77: every particle starts from W(0; h[0]) -- not m_i * W(0; h_i)
     const double rho = qn + sum;
     rho_out[orig] = rho;
@@ -599,8 +609,8 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
                                               const double *__restrict__ vel4,
                                               const int32_t *__restrict__ perm,
                                               const double *__restrict__ h_orig,
-                                              const int32_t *__restrict__ row, int count, int orig, int self,
-                                              double px, double py, double pz, double vx, double vy,
+                                              const int32_t *__restrict__ row, size_t stride, int count,
+                                              int orig, int self, double px, double py, double pz, double vx, double vy,
                                               double vz, double Ai, double hinv, double c2,
                                               double fcutsq, bool two_d)
 {
@@ -608,7 +618,7 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
     const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
     int jn[kRowUF];
 #pragma unroll
-    for (int u = 0; u < kRowUF; ++u) jn[u] = u < count ? row[(size_t)u * 32] : self;
+    for (int u = 0; u < kRowUF; ++u) jn[u] = u < count ? row[(size_t)u * stride] : self;
     for (int k0 = 0; k0 < count; k0 += kRowUF) {
         double bx[kRowUF], by[kRowUF], bz[kRowUF], bm[kRowUF], wx[kRowUF], wy[kRowUF], wz[kRowUF], Aj[kRowUF];
         int j[kRowUF];
@@ -621,7 +631,7 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
             const int kn = k0 + kRowUF + u;
-            jn[u] = kn < count ? row[(size_t)kn * 32] : self;
+            jn[u] = kn < count ? row[(size_t)kn * stride] : self;
         }
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
@@ -661,7 +671,7 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
     return f;
 }
 
-template <bool UNIFORM_H>
+template <bool UNIFORM_H, int LPP>
 __global__ void __launch_bounds__(kBlock)
 force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__restrict__ pos4,
              const double *__restrict__ vel4, const float *__restrict__ rel4,
@@ -670,7 +680,8 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
              const double *__restrict__ h_orig, int list_fresh, double fcutsq, int dim,
              double *__restrict__ vdot, double *__restrict__ udot)
 {
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int a = gt / LPP, q = gt % LPP;
     const bool active = a < n;
     double px = 0, py = 0, pz = 0, pm = 0, vx = 0, vy = 0, vz = 0, Ai = 0;
     int count = 0, orig = 0;
@@ -686,11 +697,19 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
     const bool skip = __all_sync(0xffffffffu, interior) && can_skip;
     const double h0 = h_orig[0];
     const double hinv = 1.0 / h0, c2 = -12.0 * lucy_norm3(h0) * hinv * hinv;
-    const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
+    const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K + q) * 32 + (a & 31);
+    const int mine = count > q ? (count - q + LPP - 1) / LPP : 0;
     ForceAcc f;
-    if (skip) f = force_row<UNIFORM_H, false>(g, pos4, vel4, perm, h_orig, row, count, orig, a, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
-    else f = force_row<UNIFORM_H, true>(g, pos4, vel4, perm, h_orig, row, count, orig, a, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
-    if (!active) return;
+    if (skip) f = force_row<UNIFORM_H, false>(g, pos4, vel4, perm, h_orig, row, (size_t)32 * LPP, mine, orig, a, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
+    else f = force_row<UNIFORM_H, true>(g, pos4, vel4, perm, h_orig, row, (size_t)32 * LPP, mine, orig, a, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
+#pragma unroll
+    for (int o = 1; o < LPP; o <<= 1) {
+        f.ax += __shfl_xor_sync(0xffffffffu, f.ax, o);
+        f.ay += __shfl_xor_sync(0xffffffffu, f.ay, o);
+        f.az += __shfl_xor_sync(0xffffffffu, f.az, o);
+        f.du += __shfl_xor_sync(0xffffffffu, f.du, o);
+    }
+    if (!active || q != 0) return;
     (void)pm;
     // the reference accumulates into vdot/udot (particles.py:549-550 zeroes them per evaluation)
     vdot[3 * (size_t)orig] += f.ax;
@@ -923,6 +942,22 @@ inline int launch_status()
     return e == cudaSuccess ? SPH_OK : (int)e;
 }
 
+// Lanes cooperating on one particle in the density / force passes.  Measured on B200 (256^3):
+// 1 lane per particle is fastest (density 2.10 ms; 2 lanes 2.52, 4 lanes 3.69, 8 lanes 5.23):
+// splitting a row over lanes makes the index loads touch LPP lines per request and buys nothing
+// on the gathers, which cost one L1 wavefront per 32-byte sector either way.  SPH_LPP=1|2|4|8 in
+// the environment selects the other instantiations for experiments.
+int lanes_per_particle()
+{
+    static int lpp = 0;
+    if (!lpp) {
+        const char *e = getenv("SPH_LPP");
+        lpp = e ? atoi(e) : 1;
+        if (lpp != 1 && lpp != 2 && lpp != 4 && lpp != 8) lpp = 1;
+    }
+    return lpp;
+}
+
 int g_sm_count = 0;
 
 int sm_count()
@@ -1138,15 +1173,20 @@ int sph_density_eos(const sph_grid *g, const sph_buffers *b, const sph_eos *eos,
     if (!use_hlr && (!d_p || !d_pco || !d_u || !d_t)) return SPH_E_BADARG;
     if (b->n == 0) return SPH_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    const int nb = blocks_for(b->n, kBlock);
-    if (h_uniform)
-        density_kernel<true><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm,
-                                                   b->nbr, b->cnt, b->status, d_h_orig, *eos, list_fresh,
-                                                   use_hlr, d_rho, d_p, d_pco, d_u, d_t);
-    else
-        density_kernel<false><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm,
-                                                    b->nbr, b->cnt, b->status, d_h_orig, *eos, list_fresh,
-                                                    use_hlr, d_rho, d_p, d_pco, d_u, d_t);
+    const int lpp = lanes_per_particle();
+#define SPH_LAUNCH_DENSITY(U, L)                                                                              \
+    density_kernel<U, L><<<blocks_for((int64_t)b->n * L, kBlock), kBlock, 0, s>>>(                            \
+        *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig, *eos, \
+        list_fresh, use_hlr, d_rho, d_p, d_pco, d_u, d_t)
+    if (h_uniform) {
+        if (lpp == 1) SPH_LAUNCH_DENSITY(true, 1);
+        else if (lpp == 2) SPH_LAUNCH_DENSITY(true, 2);
+        else if (lpp == 8) SPH_LAUNCH_DENSITY(true, 8);
+        else SPH_LAUNCH_DENSITY(true, 4);
+    } else {
+        SPH_LAUNCH_DENSITY(false, 1);
+    }
+#undef SPH_LAUNCH_DENSITY
     return launch_status();
 }
 
@@ -1162,12 +1202,20 @@ int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, co
     if (d_press)
         pressure_term_kernel<<<nb, kBlock, 0, s>>>(b->n, b->perm, d_press, d_rho, b->vel4);
     const double fcutsq = fcutoff * fcutoff;                // forces.py:36
-    if (h_uniform)
-        force_kernel<true><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr,
-                                                 b->cnt, b->status, d_h_orig, list_fresh, fcutsq, dim, d_vdot, d_udot);
-    else
-        force_kernel<false><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr,
-                                                  b->cnt, b->status, d_h_orig, list_fresh, fcutsq, dim, d_vdot, d_udot);
+    const int lpp = lanes_per_particle();
+#define SPH_LAUNCH_FORCE(U, L)                                                                                 \
+    force_kernel<U, L><<<blocks_for((int64_t)b->n * L, kBlock), kBlock, 0, s>>>(                               \
+        *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig,        \
+        list_fresh, fcutsq, dim, d_vdot, d_udot)
+    if (h_uniform) {
+        if (lpp == 1) SPH_LAUNCH_FORCE(true, 1);
+        else if (lpp == 2) SPH_LAUNCH_FORCE(true, 2);
+        else if (lpp == 8) SPH_LAUNCH_FORCE(true, 8);
+        else SPH_LAUNCH_FORCE(true, 4);
+    } else {
+        SPH_LAUNCH_FORCE(false, 1);
+    }
+#undef SPH_LAUNCH_FORCE
     return launch_status();
 }
 
