@@ -43,26 +43,30 @@ class SphEvaluator(object):
         self.h_uniform = properties._h_uniform(p, p.h)
         self._planned = True
 
-    def evaluate(self, timed=False):
+    def evaluate(self, timed=False, io=None):
+        """One derivative evaluation.  `io` (dict of tensors r v m h t rho p pco u vdot udot) selects
+        other input/output buffers than the particle system's own (used by the streamed e2e path)."""
         if not self._planned:
             self._plan()
         p, be = self.p, self.nl.backend
+        x = io if io is not None else {k: getattr(p, k) for k in ("r", "v", "m", "h", "t", "rho", "p", "pco", "u",
+                                                                    "vdot", "udot")}
         ev = None
         if timed:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             ev[0].record()
-        be.cells_and_gather(p.r, p.v, p.m)
+        be.cells_and_gather(x["r"], x["v"], x["m"])
         if timed:
             ev[1].record()
         be.nlist()
         if timed:
             ev[2].record()
-        p.vdot.zero_()
-        p.udot.zero_()
-        be.density_eos(self.eos, p.h, self.h_uniform, p.rho, p.p, p.pco, p.u, p.t)
+        x["vdot"].zero_()
+        x["udot"].zero_()
+        be.density_eos(self.eos, x["h"], self.h_uniform, x["rho"], x["p"], x["pco"], x["u"], x["t"])
         if timed:
             ev[3].record()
-        be.force(None, None, p.h, self.h_uniform, self.force.cutoff, 3, p.vdot, p.udot, reuse_press=True)
+        be.force(None, None, x["h"], self.h_uniform, self.force.cutoff, 3, x["vdot"], x["udot"], reuse_press=True)
         if timed:
             ev[4].record()
             self._events.append(ev)
@@ -101,33 +105,62 @@ class SphEvaluator(object):
 
     # ------------------------------------------------------------------ end to end with host buffers
     def run_e2e(self, steps, warmup):
-        """Every step: pinned-host r, v, m, h, t -> device; evaluate; rho, p, vdot, udot -> pinned host."""
+        """Host-buffer path: every step copies that step's r, v, m, h, t from pinned host memory to
+        the device, evaluates, and copies rho, p, vdot, udot back to pinned host memory.  Frames are
+        independent, so the three stages run as a pipeline over two device slots (copy-in of frame
+        k+1 and copy-out of frame k-1 overlap the kernels of frame k on separate streams)."""
         p = self.p
-        ins = [p.r, p.v, p.m, p.h, p.t]
-        outs = [p.rho, p.p, p.vdot, p.udot]
-        h_in = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in ins]
-        h_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
-        h2d = sum(t.numel() * t.element_size() for t in ins)
-        d2h = sum(t.numel() * t.element_size() for t in outs)
+        ins, outs, alls = ("r", "v", "m", "h", "t"), ("rho", "p", "vdot", "udot"), \
+            ("r", "v", "m", "h", "t", "rho", "p", "pco", "u", "vdot", "udot")
+        base = {k: getattr(p, k).as_subclass(torch.Tensor) for k in alls}
+        slots = [base, {k: torch.empty_like(v) for k, v in base.items()}]
+        h_in = {k: torch.empty(base[k].shape, dtype=base[k].dtype, pin_memory=True).copy_(base[k]) for k in ins}
+        h_out = {k: torch.empty(base[k].shape, dtype=base[k].dtype, pin_memory=True) for k in outs}
+        h2d = sum(h_in[k].numel() * h_in[k].element_size() for k in ins)
+        d2h = sum(h_out[k].numel() * h_out[k].element_size() for k in outs)
+        s_comp = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        comp_done = [None, None]
+        out_done = [None, None]
 
-        def one():
-            for d, h in zip(ins, h_in):
-                d.as_subclass(torch.Tensor).copy_(h, non_blocking=True)
-            self.evaluate()
-            for d, h in zip(outs, h_out):
-                h.copy_(d.as_subclass(torch.Tensor), non_blocking=True)
+        def frame(k):
+            sl = slots[k % 2]
+            with torch.cuda.stream(s_in):
+                if comp_done[k % 2] is not None:
+                    s_in.wait_event(comp_done[k % 2])          # slot inputs no longer being read
+                for name in ins:
+                    sl[name].copy_(h_in[name], non_blocking=True)
+                in_done = torch.cuda.Event()
+                in_done.record(s_in)
+            s_comp.wait_event(in_done)
+            if out_done[k % 2] is not None:
+                s_comp.wait_event(out_done[k % 2])             # slot outputs already copied out
+            self.evaluate(io=sl)
+            comp_done[k % 2] = torch.cuda.Event()
+            comp_done[k % 2].record(s_comp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(comp_done[k % 2])
+                for name in outs:
+                    h_out[name].copy_(sl[name], non_blocking=True)
+                out_done[k % 2] = torch.cuda.Event()
+                out_done[k % 2].record(s_out)
 
-        for _ in range(warmup):
-            one()
+        for k in range(warmup):
+            frame(k)
         torch.cuda.synchronize()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            one()
-        e1.record()
+        comp_done[:] = [None, None]
+        out_done[:] = [None, None]
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(s_comp)
+        s_in.wait_event(t0)
+        for k in range(steps):
+            frame(k)
+        s_comp.wait_stream(s_out)
+        s_comp.wait_stream(s_in)
+        t1.record(s_comp)
         torch.cuda.synchronize()
-        return {"ms": e0.elapsed_time(e1), "steps": steps, "h2d": h2d, "d2h": d2h}
+        return {"ms": t0.elapsed_time(t1), "steps": steps, "h2d": h2d, "d2h": d2h}
 
 
 def p_ver(t):
