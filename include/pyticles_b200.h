@@ -76,7 +76,8 @@ typedef struct sph_grid {
     uint32_t ncode;      /* number of cell codes = 1 << (total bits) */
     float thr_in;        /* fp32 pre-filter: rsq32 <  thr_in  => certainly inside  */
     float thr_out;       /*                  rsq32 >= thr_out => certainly outside */
-    int32_t reserved[4];
+    uint32_t top[3];     /* Morton-dilated code bits of the last local layer, pdep(ncl-1, mask) */
+    int32_t reserved;
 } sph_grid;
 
 /* Equation of state constants (properties.py:18-20; feos.eos.{adash,bdash,kbdash}). */

@@ -44,7 +44,8 @@ class SphGrid(ctypes.Structure):
                 ("ncode", ctypes.c_uint32),
                 ("thr_in", ctypes.c_float),
                 ("thr_out", ctypes.c_float),
-                ("reserved", ctypes.c_int32 * 4)]
+                ("top", c_uint3),
+                ("reserved", ctypes.c_int32)]
 
 
 class SphEos(ctypes.Structure):

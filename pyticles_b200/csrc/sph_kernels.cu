@@ -323,35 +323,51 @@ nlist_kernel(const __grid_constant__ sph_grid g, int n, int K,
     for (uint32_t c = blockIdx.x * kNlWarps + wib; c < g.ncode; c += nwarps) {
         const uint32_t cs = cell_start[c], ce = cell_start[c + 1];
         if (cs == ce) continue;
-        const int cx = (int)pext32(c, g.mask[0]), cy = (int)pext32(c, g.mask[1]),
-                  cz = (int)pext32(c, g.mask[2]);
         uint32_t nstart = 0, ncount = 0;
         float fx = 0.f, fy = 0.f, fz = 0.f;
         if (lane < 27) {
             int o[3] = {lane % 3 - 1, (lane / 3) % 3 - 1, lane / 9 - 1};
-            const int cc[3] = {cx, cy, cz};
-            int nb[3];
             bool ok = true;
+            uint32_t code = 0;
+            if (!SMALL) {
+                // neighbour cell codes by dilated-integer arithmetic on the Morton code itself:
+                // +1 is ((part | ~mask) + 1) & mask, -1 is (part - 1) & mask; no decode needed
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                if (!SMALL || g.ncl[d] >= 3) {
-                    int t = cc[d] + o[d];
-                    if (t < 0 || t >= g.ncl[d]) {
-                        if (g.wrap[d]) t += (t < 0) ? g.ncl[d] : -g.ncl[d];
-                        else ok = false;
+                for (int d = 0; d < 3; ++d) {
+                    const uint32_t m = g.mask[d], part = c & m;
+                    uint32_t np = part;
+                    if (o[d] > 0) {
+                        if (part == g.top[d]) { np = 0; ok = ok && g.wrap[d]; }
+                        else np = ((part | ~m) + 1u) & m;
+                    } else if (o[d] < 0) {
+                        if (part == 0) { np = g.top[d]; ok = ok && g.wrap[d]; }
+                        else np = (part - 1u) & m;
                     }
-                    nb[d] = t;
-                } else {                          // 1 or 2 layers: visit each layer once
-                    const int t = o[d] + 1;
-                    if (t >= g.ncl[d]) ok = false;
-                    nb[d] = t;
-                    o[d] = t - cc[d];
+                    code |= np;
                 }
+            } else {
+                const int cc[3] = {(int)pext32(c, g.mask[0]), (int)pext32(c, g.mask[1]), (int)pext32(c, g.mask[2])};
+                int nb[3];
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    if (g.ncl[d] >= 3) {
+                        int t = cc[d] + o[d];
+                        if (t < 0 || t >= g.ncl[d]) {
+                            if (g.wrap[d]) t += (t < 0) ? g.ncl[d] : -g.ncl[d];
+                            else ok = false;
+                        }
+                        nb[d] = t;
+                    } else {                          // 1 or 2 layers: visit each layer once
+                        const int t = o[d] + 1;
+                        if (t >= g.ncl[d]) ok = false;
+                        nb[d] = t;
+                        o[d] = t - cc[d];
+                    }
+                }
+                code = pdep32((uint32_t)nb[0], g.mask[0]) | pdep32((uint32_t)nb[1], g.mask[1]) |
+                       pdep32((uint32_t)nb[2], g.mask[2]);
             }
             if (ok) {
-                const uint32_t code = pdep32((uint32_t)nb[0], g.mask[0]) |
-                                      pdep32((uint32_t)nb[1], g.mask[1]) |
-                                      pdep32((uint32_t)nb[2], g.mask[2]);
                 nstart = cell_start[code];
                 ncount = cell_start[code + 1] - nstart;
                 fx = (float)((double)o[0] * g.w[0]);
@@ -372,11 +388,22 @@ nlist_kernel(const __grid_constant__ sph_grid g, int n, int K,
         for (uint32_t wbase = 0; wbase < total; wbase += kNlWin) {
             __syncwarp();
             // every lane copies the particles of the neighbour cell it owns
-            for (uint32_t t = 0; t < maxc; ++t) {
-                const uint32_t s = prefix + t - wbase;          // wraps below the window: fails s < kNlWin
-                if (t < ncount && s < (uint32_t)kNlWin) {
-                    const float4 p = __ldg(rel + nstart + t);
-                    S[s] = make_float4(p.x + fx, p.y + fy, p.z + fz, __int_as_float((int)(nstart + t)));
+            if (total <= (uint32_t)kNlWin) {                    // the usual case: one window
+                const float4 *src = rel + nstart;
+                float4 *dst = S + prefix;
+                for (uint32_t t = 0; t < maxc; ++t) {
+                    if (t < ncount) {
+                        const float4 p = __ldg(src + t);
+                        dst[t] = make_float4(p.x + fx, p.y + fy, p.z + fz, __int_as_float((int)(nstart + t)));
+                    }
+                }
+            } else {
+                for (uint32_t t = 0; t < maxc; ++t) {
+                    const uint32_t s = prefix + t - wbase;      // wraps below the window: fails s < kNlWin
+                    if (t < ncount && s < (uint32_t)kNlWin) {
+                        const float4 p = __ldg(rel + nstart + t);
+                        S[s] = make_float4(p.x + fx, p.y + fy, p.z + fz, __int_as_float((int)(nstart + t)));
+                    }
                 }
             }
             const uint32_t nS = min((uint32_t)kNlWin, total - wbase);
@@ -988,6 +1015,38 @@ int64_t sph_nbr_elems(int32_t n, int32_t max_nbrs)
     return (((int64_t)n + 31) / 32) * 32 * (int64_t)max_nbrs;
 }
 
+static uint32_t host_pdep(uint32_t v, uint32_t mask)
+{
+    uint32_t r = 0;
+    for (uint32_t bit = 1; mask; bit <<= 1) {
+        const uint32_t low = mask & (0u - mask);
+        if (v & 1u) r |= low;
+        v >>= 1;
+        mask ^= low;
+        (void)bit;
+    }
+    return r;
+}
+
+static void grid_set_codes(sph_grid *g)
+{
+    int bits[3], total_bits = 0;
+    for (int d = 0; d < 3; ++d) {
+        bits[d] = 0;
+        while ((1 << bits[d]) < g->ncl[d]) ++bits[d];
+        total_bits += bits[d];
+    }
+    // generalised Morton code: deal the bits of x, y, z round-robin while each has bits left
+    g->mask[0] = g->mask[1] = g->mask[2] = 0;
+    int used[3] = {0, 0, 0}, out = 0;
+    while (out < total_bits)
+        for (int d = 0; d < 3; ++d)
+            if (used[d] < bits[d]) { g->mask[d] |= 1u << out; ++out; ++used[d]; }
+    g->ncode = 1u << total_bits;
+    for (int d = 0; d < 3; ++d) g->top[d] = host_pdep((uint32_t)(g->ncl[d] - 1), g->mask[d]);
+    g->reserved = 0;
+}
+
 int sph_grid_plan(const double box[3], double cutoff, double tolerance, int64_t n_hint,
                   const double *occ_lo, const double *occ_hi, sph_grid *g)
 {
@@ -1032,7 +1091,7 @@ int sph_grid_plan(const double box[3], double cutoff, double tolerance, int64_t 
         }
     }
     double wmax = 0.0;
-    int bits[3], total_bits = 0;
+    int total_bits = 0;
     for (int d = 0; d < 3; ++d) {
         g->w[d] = box[d] / g->nc[d];
         g->inv_w[d] = g->nc[d] / box[d];
@@ -1040,18 +1099,12 @@ int sph_grid_plan(const double box[3], double cutoff, double tolerance, int64_t 
         g->ncl[d] = g->nc[d];
         g->wrap[d] = 1;
         if (g->w[d] > wmax) wmax = g->w[d];
-        bits[d] = 0;
-        while ((1 << bits[d]) < g->ncl[d]) ++bits[d];
-        total_bits += bits[d];
+        int b = 0;
+        while ((1 << b) < g->ncl[d]) ++b;
+        total_bits += b;
     }
     if (total_bits > 30) return SPH_E_TOOBIG;
-    // generalised Morton code: deal the bits of x, y, z round-robin while each has bits left
-    g->mask[0] = g->mask[1] = g->mask[2] = 0;
-    int used[3] = {0, 0, 0}, out = 0;
-    while (out < total_bits)
-        for (int d = 0; d < 3; ++d)
-            if (used[d] < bits[d]) { g->mask[d] |= 1u << out; ++out; ++used[d]; }
-    g->ncode = 1u << total_bits;
+    grid_set_codes(g);
     // fp32 pre-filter band.  Cell-relative coordinates carry an absolute error of at most
     // ~4 * 2^-24 * wmax per component after the shift and the subtraction; rsq inherits
     // 2*sqrt(3)*rl*err + 3*err^2 plus ~8*2^-24 relative from its own arithmetic.  Use 4x that.
@@ -1064,7 +1117,6 @@ int sph_grid_plan(const double box[3], double cutoff, double tolerance, int64_t 
     if (!(tin > 0.0f)) tin = 0.0f;
     g->thr_in = tin;
     g->thr_out = tout;
-    for (int k = 0; k < 4; ++k) g->reserved[k] = 0;
     return SPH_OK;
 }
 
@@ -1076,18 +1128,7 @@ int sph_grid_restrict_x(sph_grid *g, int32_t first_layer, int32_t n_layers)
     g->lo[0] = first_layer;
     g->ncl[0] = n_layers;
     g->wrap[0] = (n_layers == g->nc[0]) ? 1 : 0;
-    int bits[3], total_bits = 0;
-    for (int d = 0; d < 3; ++d) {
-        bits[d] = 0;
-        while ((1 << bits[d]) < g->ncl[d]) ++bits[d];
-        total_bits += bits[d];
-    }
-    g->mask[0] = g->mask[1] = g->mask[2] = 0;
-    int used[3] = {0, 0, 0}, out = 0;
-    while (out < total_bits)
-        for (int d = 0; d < 3; ++d)
-            if (used[d] < bits[d]) { g->mask[d] |= 1u << out; ++out; ++used[d]; }
-    g->ncode = 1u << total_bits;
+    grid_set_codes(g);
     return SPH_OK;
 }
 
