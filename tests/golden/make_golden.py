@@ -142,5 +142,39 @@ def main():
     print("maintain_343           build=%d compress=%d rebuild=%s" % (iap0.shape[0], nl.nip, nl.rebuild_list))
 
 
+def c1_trajectory():
+    """BASELINE config 1 restated with in-repo arithmetic: 20x20x1 sheet,
+    VerletList(cutoff=2, tolerance=1) built once, pure-Python spam_properties + forces.SpamForce,
+    imp_euler, dt=0.05.  Separations go through the fp64 base class (NeighbourList.separations)
+    so the trajectory is the self-consistent fp64 one."""
+    r, v = lattice(20, 20, 1, 20261)
+    n = r.shape[0]
+    particles.SPROPS = True
+    p = particles.SmoothParticleSystem(n, d=3, maxn=n, xmax=20., ymax=20., zmax=20., hshort=2.0, hlong=4.0,
+                                       integrator='ieuler')
+    p.r[:, :] = r
+    p.v[:, :] = v
+    nl = neighbour_list.VerletList(p, cutoff=2.0, tolerance=1.0)
+    nl.separations = lambda: neighbour_list.NeighbourList.separations(nl)
+    p.nlists.append(nl)
+    p.nl_default = nl
+    p.forces.append(forces.SpamForce(p, nl))
+    nl.build()
+    nl.separations()
+    properties.spam_properties(p, nl)
+    out = dict(r0=r, v0=v, dt=0.05)
+    for step in range(1, 21):
+        p.update(0.05)
+        if step in (1, 5, 20):
+            out["r%d" % step] = p.r.copy()
+            out["v%d" % step] = p.v.copy()
+            out["rho%d" % step] = p.rho.copy()
+            out["u%d" % step] = p.u.copy()
+    particles.SPROPS = False
+    np.savez_compressed(os.path.join(HERE, "c1_trajectory.npz"), **out)
+    print("c1_trajectory          20 steps, max|v|=%.4f" % np.abs(p.v).max())
+
+
 if __name__ == "__main__":
     main()
+    c1_trajectory()

@@ -320,3 +320,35 @@ def test_update_step_matches_oracle_integrator():
     v2 = v + (o1b["vdot"] * dt + o2["vdot"] * dt) / 2
     assert rel_err(_np(p.v)[:n], v2) < 1e-9
     assert rel_err(_np(p.r)[:n], np.where(r2 > np.array(box), 0.0, np.where(r2 < 0, np.array(box), r2))) < 1e-12
+
+
+def test_c1_trajectory_matches_reference(golden_dir):
+    """BASELINE config 1: the reference's own 20x20x1 sheet run -- list built
+    once, SPROPS properties + SpamForce, imp_euler, MirrorBox -- against this backend driven by the
+    same statements.  <= 1e-10 after step 1; the bound is relaxed as the trajectory diverges
+    (<= 1e-8 at step 5, <= 1e-6 at step 20)."""
+    from pyticles_b200 import forces, neighbour_list, particles, properties
+    g = np.load(os.path.join(golden_dir, "c1_trajectory.npz"))
+    r, v = g["r0"], g["v0"]
+    n = r.shape[0]
+    particles.SPROPS = True
+    try:
+        p = particles.SmoothParticleSystem(n, d=3, maxn=n, xmax=20., ymax=20., zmax=20., hshort=2.0, hlong=4.0,
+                                           integrator='ieuler')
+        p.r[:, :] = r
+        p.v[:, :] = v
+        nl = neighbour_list.VerletList(p, cutoff=2.0, tolerance=1.0)
+        p.nlists.append(nl)
+        p.nl_default = nl
+        p.forces.append(forces.SpamForce(p, nl))
+        nl.build()
+        nl.separations()
+        properties.spam_properties(p, nl)
+        tol = {1: 1e-10, 5: 1e-8, 20: 1e-6}
+        for step in range(1, 21):
+            p.update(float(g["dt"]))
+            if step in tol:
+                for name in ("r", "v", "rho", "u"):
+                    assert rel_err(_np(getattr(p, name)), g["%s%d" % (name, step)]) < tol[step], (name, step)
+    finally:
+        particles.SPROPS = False
