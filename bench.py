@@ -302,7 +302,9 @@ def main():
     step_bytes = (216.0 + 8.0 * pairs) * n_local
     roof = {"bound": "hbm", "kernel": sim.kernel_names[dom], "pass": dom,
             "achieved": pass_out[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-            "frac": pass_out[dom]["frac"], "traffic": sim.ncu_traffic.get(dom),
+            "frac": pass_out[dom]["frac"],
+            "traffic": sim.ncu_traffic.get(dom) if (args.workload == "c3" and world == 1) else None,
+            "algorithmic_bytes": round(alg[dom] * n_local, 1),
             "peak_source": peak_src,
             "whole_step": {"alg_bytes_per_particle": round(216.0 + 8.0 * pairs, 1),
                            "achieved_gbs": round(step_bytes / (ms / args.steps * 1e-3) / 1e9, 1),
