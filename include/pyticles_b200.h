@@ -165,6 +165,13 @@ int sph_force(const sph_grid *grid, const sph_buffers *buf, const double *d_pres
               const double *d_rho, const double *d_h_orig, int h_uniform, int list_fresh,
               double fcutoff, int dim, double *d_vdot, double *d_udot, void *stream);
 
+/* Heat conduction from the full heat-flux vector: c_forces.SpamConduction.apply
+ * (c_forces.pyx:196-239).  d_jq[n,3] and d_rho[n] are in original order; d_aux4 is caller-owned
+ * scratch of n*4 doubles (32-byte aligned).  ACCUMULATES into udot[n] (original order). */
+int sph_conduction(const sph_grid *grid, const sph_buffers *buf, const double *d_jq, const double *d_rho,
+                   const double *d_h_orig, int h_uniform, int list_fresh, double *d_aux4, double *d_udot,
+                   void *stream);
+
 /* ------------------------------------------------------------------ pair-list API surface */
 
 /* Lexicographic i<j pair list in ORIGINAL indices (what VerletList.build leaves in

@@ -175,6 +175,13 @@ class NeighbourBackend(object):
                                  int(bool(h_uniform)), int(self.fresh), float(fcutoff), int(dim),
                                  _ptr(_f64(vdot, "vdot")), _ptr(_f64(udot, "udot")), _stream()), "sph_force")
 
+    def conduction(self, jq, rho, h, h_uniform, udot):
+        aux4 = self._alloc("aux4", 4 * self.n, torch.float64)
+        check(self.lib.sph_conduction(ctypes.byref(self.grid), ctypes.byref(self.buf), _ptr(_f64(jq, "jq")),
+                                      _ptr(_f64(rho, "rho")), _ptr(_f64(h, "h")), int(bool(h_uniform)),
+                                      int(self.fresh), _ptr(aux4), _ptr(_f64(udot, "udot")), _stream()),
+              "sph_conduction")
+
     def compress(self):
         check(self.lib.sph_compress(ctypes.byref(self.grid), ctypes.byref(self.buf), _stream()), "sph_compress")
 

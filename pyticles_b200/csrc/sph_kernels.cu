@@ -745,6 +745,106 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
     udot[orig] += f.du;
 }
 
+// ------------------------------------------------------------------ heat conduction (c_forces.pyx:196-239)
+__global__ void __launch_bounds__(kBlock)
+flux_term_kernel(int n, const int32_t *__restrict__ perm, const double *__restrict__ jq,
+                 const double *__restrict__ rho, double *__restrict__ aux4)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const size_t o = (size_t)perm[a];
+    const double d = rho[o], inv = 1.0 / (d * d);
+    store4(aux4 + 4 * (size_t)a, jq[3 * o] * inv, jq[3 * o + 1] * inv, jq[3 * o + 2] * inv, 0.0);   // q / rho^2
+}
+
+template <bool UNIFORM_H, bool WRAP>
+__device__ __forceinline__ double conduction_row(const sph_grid &g, const double *__restrict__ pos4,
+                                                 const double *__restrict__ aux4,
+                                                 const int32_t *__restrict__ perm,
+                                                 const double *__restrict__ h_orig,
+                                                 const int32_t *__restrict__ row, int count, int orig, int self,
+                                                 double px, double py, double pz, double qx, double qy,
+                                                 double qz, double hinv, double c2)
+{
+    double acc = 0.0;
+    const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
+    int jn[kRowUF];
+#pragma unroll
+    for (int u = 0; u < kRowUF; ++u) jn[u] = u < count ? row[(size_t)u * 32] : self;
+    for (int k0 = 0; k0 < count; k0 += kRowUF) {
+        double bx[kRowUF], by[kRowUF], bz[kRowUF], bm[kRowUF], ex[kRowUF], ey[kRowUF], ez[kRowUF], ew[kRowUF];
+        int j[kRowUF];
+#pragma unroll
+        for (int u = 0; u < kRowUF; ++u) {
+            j[u] = jn[u];
+            load4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
+            load4(aux4 + 4 * (size_t)j[u], ex[u], ey[u], ez[u], ew[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kRowUF; ++u) {
+            const int kn = k0 + kRowUF + u;
+            jn[u] = kn < count ? row[(size_t)kn * 32] : self;
+        }
+#pragma unroll
+        for (int u = 0; u < kRowUF; ++u) {
+            double dx = bx[u] - px, dy = by[u] - py, dz = bz[u] - pz;
+            if (WRAP) {
+                dx = min_image(dx, g.box[0], hx);
+                dy = min_image(dy, g.box[1], hy);
+                dz = min_image(dz, g.box[2], hz);
+            }
+            const double rr = sqrt(rsq_exact(dx, dy, dz));
+            double hi = hinv, cc = c2;
+            if (!UNIFORM_H) {
+                const int oj = perm[j[u]];
+                const double h = h_orig[oj < orig ? oj : orig];
+                hi = 1.0 / h;
+                cc = -12.0 * lucy_norm3(h) * hi * hi;
+            }
+            const double s = rr * hi;
+            if (s < 1.0 && k0 + u < count) {
+                const double t = 1.0 - s;
+                const double fac = cc * (t * t);                       // dW/dx_a = fac * dx_a
+                // c_forces.pyx:228-237 seen from this particle: udot_self -= sum_a (Q_self + Q_other)_a dW_a m_other
+                acc -= (((qx + ex[u]) * (fac * dx) + (qy + ey[u]) * (fac * dy)) + (qz + ez[u]) * (fac * dz)) * bm[u];
+            }
+        }
+    }
+    return acc;
+}
+
+template <bool UNIFORM_H>
+__global__ void __launch_bounds__(kBlock)
+conduction_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__restrict__ pos4,
+                  const double *__restrict__ aux4, const float *__restrict__ rel4,
+                  const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
+                  const int32_t *__restrict__ cnt, const sph_status *__restrict__ status,
+                  const double *__restrict__ h_orig, int list_fresh, double *__restrict__ udot)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = a < n;
+    double px = 0, py = 0, pz = 0, pm = 0, qx = 0, qy = 0, qz = 0, qw = 0;
+    int count = 0, orig = 0;
+    bool interior = true;
+    if (active) {
+        load4(pos4 + 4 * (size_t)a, px, py, pz, pm);
+        load4(aux4 + 4 * (size_t)a, qx, qy, qz, qw);
+        count = min(cnt[a], K);
+        orig = perm[a];
+        interior = cell_is_interior(g, __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w));
+    }
+    const bool can_skip = list_fresh && !(status->flags & (SPH_F_OUT_OF_BOX | SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
+    const bool skip = __all_sync(0xffffffffu, interior) && can_skip;
+    const double h0 = h_orig[0];
+    const double hinv = 1.0 / h0, c2 = -12.0 * lucy_norm3(h0) * hinv * hinv;
+    const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
+    double acc;
+    if (skip) acc = conduction_row<UNIFORM_H, false>(g, pos4, aux4, perm, h_orig, row, count, orig, a, px, py, pz, qx, qy, qz, hinv, c2);
+    else acc = conduction_row<UNIFORM_H, true>(g, pos4, aux4, perm, h_orig, row, count, orig, a, px, py, pz, qx, qy, qz, hinv, c2);
+    (void)pm; (void)qw;
+    if (active) udot[orig] += acc;
+}
+
 // ------------------------------------------------------------------ list maintenance / export
 __global__ void __launch_bounds__(kBlock)
 compress_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__restrict__ pos4,
@@ -1257,6 +1357,24 @@ int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, co
         SPH_LAUNCH_FORCE(false, 1);
     }
 #undef SPH_LAUNCH_FORCE
+    return launch_status();
+}
+
+int sph_conduction(const sph_grid *g, const sph_buffers *b, const double *d_jq, const double *d_rho,
+                   const double *d_h_orig, int h_uniform, int list_fresh, double *d_aux4, double *d_udot,
+                   void *stream)
+{
+    if (!g || !b || !d_jq || !d_rho || !d_h_orig || !d_aux4 || !d_udot) return SPH_E_BADARG;
+    if (b->n == 0) return SPH_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nb = blocks_for(b->n, kBlock);
+    flux_term_kernel<<<nb, kBlock, 0, s>>>(b->n, b->perm, d_jq, d_rho, d_aux4);
+    if (h_uniform)
+        conduction_kernel<true><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, d_aux4, b->rel4, b->perm, b->nbr,
+                                                      b->cnt, b->status, d_h_orig, list_fresh, d_udot);
+    else
+        conduction_kernel<false><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, d_aux4, b->rel4, b->perm, b->nbr,
+                                                       b->cnt, b->status, d_h_orig, list_fresh, d_udot);
     return launch_status();
 }
 

@@ -4,6 +4,7 @@
     SpamForce(p, nl, cutoff=5.0)                   forces.py:321-368, c_forces.pyx:54-115
     CohesiveSpamForce(p, nl, cutoff=10.0)          forces.py:371-405, c_forces.pyx:125-182
     SpamForce2d / CohesiveSpamForce2d              forces.py:246-318
+    SpamConduction(p, nl)                          c_forces.pyx:185-239
 
 `apply()` runs the CUDA force pass (sph_force) over the neighbour structure and ACCUMULATES
 into p.vdot / p.udot, so several forces stack exactly as in the reference
@@ -102,3 +103,17 @@ class CohesiveSpamForce2d(_SpamBase):
 
     def __init__(self, particles, neighbour_list, cutoff=10.0):
         Force.__init__(self, particles, neighbour_list, cutoff=cutoff)
+
+
+class SpamConduction(Force):
+    """Heat conduction using the full heat flux vector p.jq (c_forces.pyx:185-239): accumulates
+    -(q_i/rho_i^2 + q_j/rho_j^2) . dW m_j into udot_i (and the mirror term into udot_j).  As in the
+    reference there is no separate cutoff: the kernel gradient vanishes beyond h."""
+
+    def __init__(self, particles, nl):
+        Force.__init__(self, particles, nl)
+
+    def apply(self):
+        p, nl = self.p, self.nl
+        nl._refresh_sorted()
+        nl.backend.conduction(p.jq, p.rho, p.h, _properties._h_uniform(p, p.h), p.udot)

@@ -52,3 +52,37 @@ def rk4(get_state, calc_derivs, get_derivs, set_state, dt):
     calc_derivs()
     c4 = get_derivs() * dt
     set_state(x_start + (1.0 / 6.0) * (c1 + 2. * c2 + 2. * c3 + c4))
+
+
+def _touch(*tensors):
+    """Kernels launched through the C ABI write through raw pointers; bump the tensors' version
+    counters so that the neighbour lists notice the particle state changed."""
+    for t in tensors:
+        t[:0].zero_()
+
+
+def fused_imp_euler(p, dt):
+    """Improved Euler for a SmoothParticleSystem without the [11, maxn] state matrices: the same
+    arithmetic as imp_euler above driven through gather_state / scatter_state (integrator.py:44-59
+    with particles.py:496-542), written directly on p.r, p.v, p.u with the sph_axpy kernel.
+    Kept identical to the generic path in what it leaves behind: rho, p, pco end at their
+    first-stage values (their state derivatives are zero, particles.py:538-540) and m is untouched."""
+    n = p.n
+    p.derivatives()                                      # stage 1: rdot = v0, vdot0, udot0
+    r0, v0, u0 = p.r[:n].clone(), p.v[:n].clone(), p.u[:n].clone()
+    vd0, ud0 = p.vdot[:n].clone(), p.udot[:n].clone()
+    keep = [getattr(p, k)[:n].clone() for k in ("rho", "p", "pco")]
+    # predictor: x = x_start + xdot * dt
+    _backend.axpy(p.r[:n], r0, v0, dt)
+    _backend.axpy(p.v[:n], v0, vd0, dt)
+    _backend.axpy(p.u[:n], u0, ud0, dt)
+    _touch(p.r, p.v, p.u)
+    p.derivatives()                                      # stage 2 at the predicted state
+    v1 = p.v[:n].clone()
+    # corrector: x = x_start + (c1 + c2) / 2
+    _backend.axpy(p.r[:n], r0, v0 + v1, 0.5 * dt)
+    _backend.axpy(p.v[:n], v0, vd0 + p.vdot[:n], 0.5 * dt)
+    _backend.axpy(p.u[:n], u0, ud0 + p.udot[:n], 0.5 * dt)
+    _touch(p.r, p.v, p.u)
+    for k, val in zip(("rho", "p", "pco"), keep):
+        getattr(p, k)[:n] = val

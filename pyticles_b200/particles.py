@@ -22,7 +22,7 @@ from . import box as _box
 from . import configuration
 from . import properties
 from .array import from_numpy, ones, zeros
-from .integrator import euler, imp_euler, rk4
+from .integrator import _touch, euler, fused_imp_euler, imp_euler, rk4
 
 XMAX = 5
 YMAX = 5
@@ -30,6 +30,7 @@ ZMAX = 1
 VMAX = 0.1
 ADVECTIVE = False
 SPROPS = False
+FUSED = False            # SmoothParticleSystem.update: improved Euler without the [11, maxn] state matrices
 DEVICE = "cuda"
 
 
@@ -108,6 +109,7 @@ class ParticleSystem(object):
         self.rebuild_lists()
         self.step(self.gather_state, self.derivatives, self.gather_derivatives, self.scatter_state, dt)
         self.box.apply(self)
+        _touch(self.r, self.v)
         self.steps += 1
 
     def gather_state(self):
@@ -197,9 +199,13 @@ class SmoothParticleSystem(ParticleSystem):
         self.derivatives()
         self.timing['deriv time'] = time() - t
         t = time()
-        self.step(self.gather_state, self.derivatives, self.gather_derivatives, self.scatter_state, dt)
+        if FUSED and self.step is imp_euler:
+            fused_imp_euler(self, dt)
+        else:
+            self.step(self.gather_state, self.derivatives, self.gather_derivatives, self.scatter_state, dt)
         self.timing['integrate time'] = time() - t
         self.box.apply(self)
+        _touch(self.r, self.v)
         if self.thermostat:
             self.apply_thermostat(self.thermostat_temp)
         self.timing['update time'] = time() - t1

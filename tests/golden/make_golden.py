@@ -175,6 +175,32 @@ def c1_trajectory():
     print("c1_trajectory          20 steps, max|v|=%.4f" % np.abs(p.v).max())
 
 
+def conduction():
+    """c_forces.SpamConduction.apply (c_forces.pyx:196-239), the compiled Cython original, on the
+    cube_729 fixture with a synthetic heat-flux field."""
+    import c_forces
+    g = np.load(os.path.join(HERE, "cube_729.npz"))
+    n = g["r"].shape[0]
+    box = g["box"]
+    p = particles.SmoothParticleSystem(n, d=3, maxn=n, xmax=box[0], ymax=box[1], zmax=box[2])
+    p.r[:, :] = g["r"]
+    p.v[:, :] = g["v"]
+    p.m[:] = g["m"]
+    p.h[:] = g["h"]
+    p.t[:] = g["t_in"]
+    nl = neighbour_list.VerletList(p, cutoff=float(g["cutoff"]), tolerance=float(g["tolerance"]))
+    nl.build()
+    neighbour_list.NeighbourList.separations(nl)
+    properties.spam_properties(p, nl)
+    rng = np.random.default_rng(20267)
+    p.jq[:, :] = rng.normal(size=(n, 3))
+    p.udot[:] = 0.0
+    c_forces.SpamConduction(p, nl).apply()
+    np.savez_compressed(os.path.join(HERE, "conduction_729.npz"), jq=p.jq.copy(), udot=p.udot.copy())
+    print("conduction_729         max|udot|=%.4e" % np.abs(p.udot).max())
+
+
 if __name__ == "__main__":
     main()
     c1_trajectory()
+    conduction()

@@ -352,3 +352,55 @@ def test_c1_trajectory_matches_reference(golden_dir):
                     assert rel_err(_np(getattr(p, name)), g["%s%d" % (name, step)]) < tol[step], (name, step)
     finally:
         particles.SPROPS = False
+
+
+def test_spam_conduction(golden_dir):
+    """c_forces.SpamConduction (c_forces.pyx:196-239): <= 1e-10 against the fp64 oracle, and within the
+    float32 temporaries of the compiled Cython original (golden from the reference itself)."""
+    from pyticles_b200 import forces, neighbour_list, properties
+    g = np.load(os.path.join(golden_dir, "cube_729.npz"))
+    c = np.load(os.path.join(golden_dir, "conduction_729.npz"))
+    box = tuple(float(x) for x in g["box"])
+    n = g["r"].shape[0]
+    p = make_system(g["r"], g["v"], g["m"], g["h"], g["t_in"], box)
+    nl = neighbour_list.VerletList(p, cutoff=float(g["cutoff"]), tolerance=float(g["tolerance"]))
+    nl.build()
+    nl.separations()
+    properties.spam_properties(p, nl)
+    p.jq[0:n, :] = c["jq"]
+    p.udot[:] = 0.0
+    forces.SpamConduction(p, nl).apply()
+    ref = O.spam_conduction(n, g["m"], c["jq"], g["rho"], g["iap"].astype(np.int64), g["dwij"])
+    assert rel_err(_np(p.udot), ref) < RTOL
+    assert rel_err(_np(p.udot), c["udot"]) < 1e-5
+
+
+def test_fused_improved_euler_equals_generic_path():
+    """particles.FUSED: the device-resident improved Euler must leave the same state as the generic
+    callback-driven integrator (integrator.py:44-59) after several updates."""
+    from pyticles_b200 import forces, neighbour_list, particles, properties
+    r, v, box = O.lattice_workload(12, 12, 12, seed=23, jitter=0.2)
+    n = r.shape[0]
+    states = []
+    particles.SPROPS = True
+    try:
+        for fused in (False, True):
+            particles.FUSED = fused
+            p = particles.SmoothParticleSystem(n, d=3, maxn=n + 7, xmax=box[0], ymax=box[1], zmax=box[2], hshort=2.0)
+            p.r[0:n, :] = r
+            p.v[0:n, :] = v
+            nl = neighbour_list.VerletList(p, cutoff=2.0, tolerance=1.0)
+            p.nlists.append(nl)
+            p.nl_default = nl
+            p.forces.append(forces.SpamForce(p, nl))
+            nl.build()
+            nl.separations()
+            properties.spam_properties(p, nl)
+            for _ in range(4):
+                p.update(0.02)
+            states.append({k: _np(getattr(p, k))[:n].copy() for k in ("r", "v", "u", "rho", "p", "pco")})
+    finally:
+        particles.FUSED = False
+        particles.SPROPS = False
+    for k in states[0]:
+        assert rel_err(states[1][k], states[0][k]) < 1e-12, k
