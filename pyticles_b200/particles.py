@@ -66,8 +66,8 @@ class ParticleSystem(object):
         v0[:, :d] = vmax * (np.random.random([maxn, d]) - 0.5)          # particles.py:123
         if rinit == 'grid':
             r0[0:n, :] = configuration.grid3d(n, side, (xmax / 2., ymax / 2., zmax / 2.), spacing=spacing)
-        elif rinit in ('fcc', 'load'):
-            raise NotImplementedError("rinit=%r: generator / NetCDF input is outside the SPH hot path" % rinit)
+        elif rinit == 'fcc':
+            raise NotImplementedError("rinit='fcc': the reference's fcc3d generator is not in its repository")
         self.r = from_numpy(r0, dev)
         self.v = from_numpy(v0, dev)
         self.m = zeros(maxn, dev)
@@ -75,6 +75,11 @@ class ParticleSystem(object):
         self.vdot = zeros((maxn, cols), dev)
         self.mdot = zeros(maxn, dev)
         self.m[:] = mass
+        if rinit == 'load':
+            # particles.py:139-143: restart from the last frame of $SPDATA/<source>
+            import os
+            from .spam_nc import read_step
+            read_step(os.path.join(os.environ.get('SPDATA', '.'), source), self, step='last')
         self.colour = 1.0, 0.0, 0.0
 
         n_variables = 7
