@@ -136,11 +136,19 @@ class SlabDecomposition(object):
         return ghosts
 
     def halo_exchange_again(self, cols):
-        """Exchange B: per-particle columns (n_own, C) of the same ghosts, in the same order."""
-        if self.world == 1:
-            return cols[:0]
-        idx, pattern = self._halo
-        out, _ = self._exchange(cols[idx], None, splits=pattern)
+        """Exchange B: per-particle columns of the same ghosts, in the same order.  `cols` is an
+        (n_own, C) tensor or a list of C per-particle vectors (gathered before stacking, so only
+        the boundary particles are touched)."""
+        idx, pattern = self._halo if self._halo is not None else (None, None)
+        if isinstance(cols, (list, tuple)):
+            if self.world == 1:
+                return cols[0].new_zeros((0, len(cols)))
+            send = torch.stack([c[idx] for c in cols], dim=1)
+        else:
+            if self.world == 1:
+                return cols[:0]
+            send = cols[idx]
+        out, _ = self._exchange(send, None, splits=pattern)
         return out
 
     def owns_pair(self, gid_i, gid_j, owned_i, owned_j):
@@ -270,7 +278,7 @@ class SlabSphEvaluator(object):
         if timed:
             ev[4].record()
         if ng:
-            pr = dec.halo_exchange_again(torch.stack([p[:no], rho[:no]], dim=1))     # B
+            pr = dec.halo_exchange_again([p[:no], rho[:no]])                         # B
             p[no:] = pr[:, 0]
             rho[no:] = pr[:, 1]
         if timed:
