@@ -165,6 +165,12 @@ int sph_force(const sph_grid *grid, const sph_buffers *buf, const double *d_pres
               const double *d_rho, const double *d_h_orig, int h_uniform, int list_fresh,
               double fcutoff, int dim, double *d_vdot, double *d_udot, void *stream);
 
+/* Refresh press_i / rho_i^2 (the operand sph_force gathers) from original-order arrays for the
+ * particles whose original index is >= first_orig only.  The slab decomposition uses it for the
+ * ghosts, whose (p, rho) arrive from the neighbouring rank after the density pass. */
+int sph_pressure_term(const sph_buffers *buf, const double *d_press, const double *d_rho, int32_t first_orig,
+                      void *stream);
+
 /* Heat conduction from the full heat-flux vector: c_forces.SpamConduction.apply
  * (c_forces.pyx:196-239).  d_jq[n,3] and d_rho[n] are in original order; d_aux4 is caller-owned
  * scratch of n*4 doubles (32-byte aligned).  ACCUMULATES into udot[n] (original order). */

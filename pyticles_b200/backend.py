@@ -175,6 +175,11 @@ class NeighbourBackend(object):
                                  int(bool(h_uniform)), int(self.fresh), float(fcutoff), int(dim),
                                  _ptr(_f64(vdot, "vdot")), _ptr(_f64(udot, "udot")), _stream()), "sph_force")
 
+    def pressure_term(self, press, rho, first_orig):
+        """vel4[., 3] = press/rho^2 for the particles with original index >= first_orig (ghosts)."""
+        check(self.lib.sph_pressure_term(ctypes.byref(self.buf), _ptr(_f64(press, "press")), _ptr(_f64(rho, "rho")),
+                                         int(first_orig), _stream()), "sph_pressure_term")
+
     def conduction(self, jq, rho, h, h_uniform, udot):
         aux4 = self._alloc("aux4", 4 * self.n, torch.float64)
         check(self.lib.sph_conduction(ctypes.byref(self.grid), ctypes.byref(self.buf), _ptr(_f64(jq, "jq")),

@@ -617,12 +617,13 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
 }
 
 __global__ void __launch_bounds__(kBlock)
-pressure_term_kernel(int n, const int32_t *__restrict__ perm, const double *__restrict__ press,
+pressure_term_kernel(int n, int first_orig, const int32_t *__restrict__ perm, const double *__restrict__ press,
                      const double *__restrict__ rho, double *__restrict__ vel4)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     const int o = perm[a];
+    if (o < first_orig) return;
     const double d = rho[o];
     vel4[4 * (size_t)a + 3] = press[o] / (d * d);
 }
@@ -1341,7 +1342,7 @@ int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, co
     cudaStream_t s = (cudaStream_t)stream;
     const int nb = blocks_for(b->n, kBlock);
     if (d_press)
-        pressure_term_kernel<<<nb, kBlock, 0, s>>>(b->n, b->perm, d_press, d_rho, b->vel4);
+        pressure_term_kernel<<<nb, kBlock, 0, s>>>(b->n, 0, b->perm, d_press, d_rho, b->vel4);
     const double fcutsq = fcutoff * fcutoff;                // forces.py:36
     const int lpp = lanes_per_particle();
 #define SPH_LAUNCH_FORCE(U, L)                                                                                 \
@@ -1357,6 +1358,16 @@ int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, co
         SPH_LAUNCH_FORCE(false, 1);
     }
 #undef SPH_LAUNCH_FORCE
+    return launch_status();
+}
+
+int sph_pressure_term(const sph_buffers *b, const double *d_press, const double *d_rho, int32_t first_orig,
+                      void *stream)
+{
+    if (!b || !d_press || !d_rho || !b->perm || !b->vel4 || first_orig < 0) return SPH_E_BADARG;
+    if (b->n > 0)
+        pressure_term_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+            b->n, first_orig, b->perm, d_press, d_rho, b->vel4);
     return launch_status();
 }
 

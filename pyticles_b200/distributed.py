@@ -183,7 +183,7 @@ class SlabSphEvaluator(object):
         vol = box[0] * box[1] * box[2]
         rl = (cutoff * cutoff + tol * tol) ** 0.5
         self.be.user_max_nbrs = int(1.6 * 4.18879 * rl ** 3 * self.n_total / vol) + 24
-        self.launches_per_eval = 12
+        self.launches_per_eval = 13     # the 11 of one GPU + slab_select + pressure_term (ghosts)
         self._events = []
         self.n_local = self.n_owned
 
@@ -281,9 +281,10 @@ class SlabSphEvaluator(object):
             pr = dec.halo_exchange_again([p[:no], rho[:no]])                         # B
             p[no:] = pr[:, 0]
             rho[no:] = pr[:, 1]
+            be.pressure_term(p, rho, no)                      # only the ghosts need their p/rho^2 refreshed
         if timed:
             ev[5].record()
-        be.force(p, rho, h, True, self.fcut, 3, vdot, udot, reuse_press=(ng == 0))
+        be.force(p, rho, h, True, self.fcut, 3, vdot, udot, reuse_press=True)
         if timed:
             ev[6].record()
             self._events.append(ev)
