@@ -72,12 +72,18 @@ typedef struct sph_grid {
     int32_t lo[3];       /* first global cell layer of the local grid (0 on one GPU) */
     int32_t ncl[3];      /* local cell layers (== nc on one GPU) */
     int32_t wrap[3];     /* 1: local grid is periodic in this dimension */
-    uint32_t mask[3];    /* bit positions of each dimension in the Morton cell code */
-    uint32_t ncode;      /* number of cell codes = 1 << (total bits) */
+    uint32_t mask[3];    /* bit positions of each dimension in the in-block Morton code */
+    uint32_t ncode;      /* number of cell codes = nblk[0]*nblk[1]*nblk[2] << lbits */
     float thr_in;        /* fp32 pre-filter: rsq32 <  thr_in  => certainly inside  */
     float thr_out;       /*                  rsq32 >= thr_out => certainly outside */
-    uint32_t top[3];     /* Morton-dilated code bits of the last local layer, pdep(ncl-1, mask) */
-    int32_t reserved;
+    uint32_t top[3];     /* in-block code bits of the last local layer of each dimension */
+    uint32_t magic0;     /* ceil(2^32 / nblk[0]): multiply-high division of the block index */
+    /* cell code = (block index << lbits) | in-block Morton code; blocks of 2^lb layers per
+     * dimension (lb <= 3), numbered row-major (x fastest) */
+    uint32_t lb[3];
+    uint32_t nblk[3];
+    uint32_t lbits;
+    uint32_t magic1;     /* ceil(2^32 / nblk[1]) */
 } sph_grid;
 
 /* Equation of state constants (properties.py:18-20; feos.eos.{adash,bdash,kbdash}). */
@@ -126,7 +132,7 @@ int64_t sph_nbr_elems(int32_t n, int32_t max_nbrs);
 
 int sph_status_reset(sph_status *d_status, void *stream);
 
-/* Cell list: counting-sort binning into Morton-ordered cells, deterministic order inside a
+/* Cell list: counting-sort binning into block-Morton-ordered cells, deterministic order inside a
  * cell (ascending original index).  Fills code, rank, cell_count, cell_start, perm.
  * First half of VerletList.build (neighbour_list.py:160-189). */
 int sph_cells_build(const sph_grid *grid, const sph_buffers *buf, const double *d_r, void *stream);

@@ -45,7 +45,11 @@ class SphGrid(ctypes.Structure):
                 ("thr_in", ctypes.c_float),
                 ("thr_out", ctypes.c_float),
                 ("top", c_uint3),
-                ("reserved", ctypes.c_int32)]
+                ("magic0", ctypes.c_uint32),
+                ("lb", c_uint3),
+                ("nblk", c_uint3),
+                ("lbits", ctypes.c_uint32),
+                ("magic1", ctypes.c_uint32)]
 
 
 class SphEos(ctypes.Structure):

@@ -89,7 +89,7 @@ class NeighbourBackend(object):
         if K is None:
             K = self.user_max_nbrs
         if K is None:
-            K = self.K if (self.K and n == self.n) else int(1.6 * self.expected_nbrs(n)) + 24
+            K = self.K if (self.K and n == self.n) else int(1.35 * self.expected_nbrs(n)) + 16
         K = max(8, min(int(K), max(n - 1, 8)))
         K = (K + 3) // 4 * 4
         self.n, self.K = int(n), K

@@ -105,7 +105,40 @@ struct CellLoc {
     uint32_t code;
     float rx, ry, rz;
     uint32_t flags;
+    bool interior;       // every dimension: >= 5 layers and not the first or last GLOBAL layer
 };
+
+// Cell code = (block index << lbits) | Morton code inside the block.  Blocks are 2^lb x 2^lb x 2^lb
+// cells (lb <= 3) numbered row-major, so the code space exceeds the real cell count by a few per
+// cent only, whatever the number of layers; inside a block the order is a (generalised) Morton curve.
+__device__ __forceinline__ uint32_t cell_code(const sph_grid &g, int cx, int cy, int cz)
+{
+    const uint32_t lx = g.lb[0], ly = g.lb[1], lz = g.lb[2];
+    const uint32_t blk = (((uint32_t)cz >> lz) * g.nblk[1] + ((uint32_t)cy >> ly)) * g.nblk[0] + ((uint32_t)cx >> lx);
+    const uint32_t loc = pdep32((uint32_t)cx & ((1u << lx) - 1u), g.mask[0]) |
+                         pdep32((uint32_t)cy & ((1u << ly) - 1u), g.mask[1]) |
+                         pdep32((uint32_t)cz & ((1u << lz) - 1u), g.mask[2]);
+    return (blk << g.lbits) | loc;
+}
+
+// blk -> (bx, by, bz) with multiply-high division: magic = ceil(2^32 / nblk) is exact here because
+// blk * nblk < 2^31 (sph_grid_plan rejects larger code spaces).
+__device__ __forceinline__ void block_coords(const sph_grid &g, uint32_t blk, uint32_t &bx, uint32_t &by, uint32_t &bz)
+{
+    const uint32_t t = g.nblk[0] == 1u ? blk : __umulhi(blk, g.magic0);
+    bx = blk - t * g.nblk[0];
+    bz = g.nblk[1] == 1u ? t : __umulhi(t, g.magic1);
+    by = t - bz * g.nblk[1];
+}
+
+__device__ __forceinline__ void cell_coords(const sph_grid &g, uint32_t code, int &cx, int &cy, int &cz)
+{
+    uint32_t bx, by, bz;
+    block_coords(g, code >> g.lbits, bx, by, bz);
+    cx = (int)((bx << g.lb[0]) | pext32(code, g.mask[0]));
+    cy = (int)((by << g.lb[1]) | pext32(code, g.mask[1]));
+    cz = (int)((bz << g.lb[2]) | pext32(code, g.mask[2]));
+}
 
 __device__ __forceinline__ int cell_coord(const sph_grid &g, int d, double x, float &rel, uint32_t &flags)
 {
@@ -131,11 +164,16 @@ __device__ __forceinline__ CellLoc locate(const sph_grid &g, double x, double y,
 {
     CellLoc c;
     c.flags = 0;
-    const int cx = cell_coord(g, 0, x, c.rx, c.flags);
-    const int cy = cell_coord(g, 1, y, c.ry, c.flags);
-    const int cz = cell_coord(g, 2, z, c.rz, c.flags);
-    c.code = pdep32((uint32_t)cx, g.mask[0]) | pdep32((uint32_t)cy, g.mask[1]) |
-             pdep32((uint32_t)cz, g.mask[2]);
+    const int cc[3] = {cell_coord(g, 0, x, c.rx, c.flags), cell_coord(g, 1, y, c.ry, c.flags),
+                       cell_coord(g, 2, z, c.rz, c.flags)};
+    c.code = cell_code(g, cc[0], cc[1], cc[2]);
+    c.interior = true;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        int cg = cc[d] + g.lo[d];
+        if (cg >= g.nc[d]) cg -= g.nc[d];
+        c.interior = c.interior && g.nc[d] >= 5 && cg >= 1 && cg <= g.nc[d] - 2;
+    }
     return c;
 }
 
@@ -279,7 +317,7 @@ gather_kernel(const __grid_constant__ sph_grid g, int n, const int32_t *__restri
     const CellLoc c = locate(g, x, y, z);
     store4(pos4 + 4 * (size_t)a, x, y, z, m[i]);
     store4(vel4 + 4 * (size_t)a, v[3 * i], v[3 * i + 1], v[3 * i + 2], 0.0);
-    reinterpret_cast<float4 *>(rel4)[a] = make_float4(c.rx, c.ry, c.rz, __uint_as_float(c.code));
+    reinterpret_cast<float4 *>(rel4)[a] = make_float4(c.rx, c.ry, c.rz, __uint_as_float(c.interior ? 1u : 0u));
 }
 
 // ------------------------------------------------------------------ neighbour pass
@@ -330,23 +368,47 @@ nlist_kernel(const __grid_constant__ sph_grid g, int n, int K,
             bool ok = true;
             uint32_t code = 0;
             if (!SMALL) {
-                // neighbour cell codes by dilated-integer arithmetic on the Morton code itself:
-                // +1 is ((part | ~mask) + 1) & mask, -1 is (part - 1) & mask; no decode needed
+                // neighbour cell codes by arithmetic on the code itself.  Inside a block: dilated-integer
+                // +1 is ((part | ~mask) + 1) & mask, -1 is (part - 1) & mask.  Across a block face the
+                // block index moves by its stride; across a box face it wraps (or the cell does not exist).
+                uint32_t loc = 0, blk = c >> g.lbits;
+                uint32_t bc[3];
+                block_coords(g, blk, bc[0], bc[1], bc[2]);
+                const uint32_t stride[3] = {1u, g.nblk[0], g.nblk[0] * g.nblk[1]};
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
                     const uint32_t m = g.mask[d], part = c & m;
+                    const bool last_blk = bc[d] == g.nblk[d] - 1u;
                     uint32_t np = part;
                     if (o[d] > 0) {
-                        if (part == g.top[d]) { np = 0; ok = ok && g.wrap[d]; }
-                        else np = ((part | ~m) + 1u) & m;
+                        if (last_blk && part == g.top[d]) {            // last layer of the grid
+                            np = 0;
+                            blk -= bc[d] * stride[d];
+                            ok = ok && g.wrap[d];
+                        } else if (part == m) {                        // last layer of the block
+                            np = 0;
+                            blk += stride[d];
+                        } else {
+                            np = ((part | ~m) + 1u) & m;
+                        }
                     } else if (o[d] < 0) {
-                        if (part == 0) { np = g.top[d]; ok = ok && g.wrap[d]; }
-                        else np = (part - 1u) & m;
+                        if (bc[d] == 0u && part == 0u) {               // first layer of the grid
+                            np = g.top[d];
+                            blk += (g.nblk[d] - 1u) * stride[d];
+                            ok = ok && g.wrap[d];
+                        } else if (part == 0u) {                       // first layer of the block
+                            np = m;
+                            blk -= stride[d];
+                        } else {
+                            np = (part - 1u) & m;
+                        }
                     }
-                    code |= np;
+                    loc |= np;
                 }
+                code = (blk << g.lbits) | loc;
             } else {
-                const int cc[3] = {(int)pext32(c, g.mask[0]), (int)pext32(c, g.mask[1]), (int)pext32(c, g.mask[2])};
+                int cc[3];
+                cell_coords(g, c, cc[0], cc[1], cc[2]);
                 int nb[3];
 #pragma unroll
                 for (int d = 0; d < 3; ++d) {
@@ -364,8 +426,7 @@ nlist_kernel(const __grid_constant__ sph_grid g, int n, int K,
                         o[d] = t - cc[d];
                     }
                 }
-                code = pdep32((uint32_t)nb[0], g.mask[0]) | pdep32((uint32_t)nb[1], g.mask[1]) |
-                       pdep32((uint32_t)nb[2], g.mask[2]);
+                code = cell_code(g, nb[0], nb[1], nb[2]);
             }
             if (ok) {
                 nstart = cell_start[code];
@@ -489,16 +550,9 @@ struct Interior {
     bool skip;   // warp-uniform: no pair of this warp can need the minimum-image shift
 };
 
-__device__ __forceinline__ bool cell_is_interior(const sph_grid &g, uint32_t code)
+__device__ __forceinline__ bool cell_is_interior(const sph_grid &, uint32_t flag)
 {
-    bool in = true;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        int cg = (int)pext32(code, g.mask[d]) + g.lo[d];
-        if (cg >= g.nc[d]) cg -= g.nc[d];
-        in = in && g.nc[d] >= 5 && cg >= 1 && cg <= g.nc[d] - 2;
-    }
-    return in;
+    return flag != 0u;       // computed once per particle by gather_kernel (rel4[., 3])
 }
 
 __device__ __forceinline__ double lucy_norm3(double h)
@@ -1129,23 +1183,35 @@ static uint32_t host_pdep(uint32_t v, uint32_t mask)
     return r;
 }
 
-static void grid_set_codes(sph_grid *g)
+static int grid_set_codes(sph_grid *g)
 {
-    int bits[3], total_bits = 0;
+    int total_bits = 0;
+    unsigned long long ncode = 1;
     for (int d = 0; d < 3; ++d) {
-        bits[d] = 0;
-        while ((1 << bits[d]) < g->ncl[d]) ++bits[d];
-        total_bits += bits[d];
+        int b = 0;
+        while ((1 << b) < g->ncl[d]) ++b;
+        g->lb[d] = (uint32_t)(b < 3 ? b : 3);                 // blocks of at most 8 layers per dimension
+        g->nblk[d] = (uint32_t)((g->ncl[d] + (1 << g->lb[d]) - 1) >> g->lb[d]);
+        total_bits += (int)g->lb[d];
+        ncode *= g->nblk[d];
     }
-    // generalised Morton code: deal the bits of x, y, z round-robin while each has bits left
+    // generalised Morton code inside a block: deal the bits of x, y, z round-robin while each has bits left
     g->mask[0] = g->mask[1] = g->mask[2] = 0;
-    int used[3] = {0, 0, 0}, out = 0;
+    uint32_t used[3] = {0, 0, 0};
+    int out = 0;
     while (out < total_bits)
         for (int d = 0; d < 3; ++d)
-            if (used[d] < bits[d]) { g->mask[d] |= 1u << out; ++out; ++used[d]; }
-    g->ncode = 1u << total_bits;
-    for (int d = 0; d < 3; ++d) g->top[d] = host_pdep((uint32_t)(g->ncl[d] - 1), g->mask[d]);
-    g->reserved = 0;
+            if (used[d] < g->lb[d]) { g->mask[d] |= 1u << out; ++out; ++used[d]; }
+    g->lbits = (uint32_t)total_bits;
+    ncode <<= total_bits;
+    if (ncode >= (1ull << 31)) return SPH_E_TOOBIG;
+    g->ncode = (uint32_t)ncode;
+    // local code bits of the last layer (inside the last block) per dimension
+    for (int d = 0; d < 3; ++d)
+        g->top[d] = host_pdep((uint32_t)((g->ncl[d] - 1) & ((1 << g->lb[d]) - 1)), g->mask[d]);
+    g->magic0 = (uint32_t)(((1ull << 32) + g->nblk[0] - 1) / g->nblk[0]);     // unused when nblk == 1
+    g->magic1 = (uint32_t)(((1ull << 32) + g->nblk[1] - 1) / g->nblk[1]);
+    return SPH_OK;
 }
 
 int sph_grid_plan(const double box[3], double cutoff, double tolerance, int64_t n_hint,
@@ -1192,7 +1258,6 @@ int sph_grid_plan(const double box[3], double cutoff, double tolerance, int64_t 
         }
     }
     double wmax = 0.0;
-    int total_bits = 0;
     for (int d = 0; d < 3; ++d) {
         g->w[d] = box[d] / g->nc[d];
         g->inv_w[d] = g->nc[d] / box[d];
@@ -1200,12 +1265,8 @@ int sph_grid_plan(const double box[3], double cutoff, double tolerance, int64_t 
         g->ncl[d] = g->nc[d];
         g->wrap[d] = 1;
         if (g->w[d] > wmax) wmax = g->w[d];
-        int b = 0;
-        while ((1 << b) < g->ncl[d]) ++b;
-        total_bits += b;
     }
-    if (total_bits > 30) return SPH_E_TOOBIG;
-    grid_set_codes(g);
+    if (grid_set_codes(g) != SPH_OK) return SPH_E_TOOBIG;
     // fp32 pre-filter band.  Cell-relative coordinates carry an absolute error of at most
     // ~4 * 2^-24 * wmax per component after the shift and the subtraction; rsq inherits
     // 2*sqrt(3)*rl*err + 3*err^2 plus ~8*2^-24 relative from its own arithmetic.  Use 4x that.
@@ -1229,8 +1290,7 @@ int sph_grid_restrict_x(sph_grid *g, int32_t first_layer, int32_t n_layers)
     g->lo[0] = first_layer;
     g->ncl[0] = n_layers;
     g->wrap[0] = (n_layers == g->nc[0]) ? 1 : 0;
-    grid_set_codes(g);
-    return SPH_OK;
+    return grid_set_codes(g);
 }
 
 int sph_status_reset(sph_status *d_status, void *stream)

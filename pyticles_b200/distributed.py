@@ -182,7 +182,7 @@ class SlabSphEvaluator(object):
         self.be = NeighbourBackend(self.device)
         vol = box[0] * box[1] * box[2]
         rl = (cutoff * cutoff + tol * tol) ** 0.5
-        self.be.user_max_nbrs = int(1.6 * 4.18879 * rl ** 3 * self.n_total / vol) + 24
+        self.be.user_max_nbrs = int(1.35 * 4.18879 * rl ** 3 * self.n_total / vol) + 16
         self.launches_per_eval = 13     # the 11 of one GPU + slab_select + pressure_term (ghosts)
         self._events = []
         self.n_local = self.n_owned

@@ -36,7 +36,7 @@ def test_exports_every_declared_symbol(lib):
 def test_struct_layout_matches_header(lib):
     from pyticles_b200 import _lib
     assert ctypes.sizeof(_lib.SphStatus) == 64
-    assert ctypes.sizeof(_lib.SphGrid) == 8 * 10 + 4 * 12 + 4 * 3 + 4 + 4 + 4 + 16
+    assert ctypes.sizeof(_lib.SphGrid) == 8 * 10 + 4 * 12 + 4 * 3 + 4 + 4 + 4 + 16 + 32
     assert ctypes.sizeof(_lib.SphEos) == 24
 
 
@@ -60,9 +60,12 @@ def test_grid_plan_cells_cover_list_radius(lib):
             assert g.nc[d] >= 1 and g.ncl[d] == g.nc[d] and g.wrap[d] == 1
             assert g.w[d] * g.nc[d] == pytest.approx(box[d], rel=1e-15)
             assert g.nc[d] == 1 or g.w[d] >= rl * (1 + 2.0 ** -21)
-            codes *= 1 << max(0, (g.nc[d] - 1).bit_length())
-        assert g.ncode == codes
-        assert g.mask[0] | g.mask[1] | g.mask[2] == g.ncode - 1
+            assert g.lb[d] == min(3, max(0, (g.nc[d] - 1).bit_length()))
+            assert g.nblk[d] == -(-g.nc[d] // (1 << g.lb[d]))
+            codes *= g.nblk[d] << g.lb[d]
+        assert g.ncode == codes and g.lbits == g.lb[0] + g.lb[1] + g.lb[2]
+        assert g.ncode < 2 * g.nc[0] * g.nc[1] * g.nc[2] + 512          # code space ~ real cell count
+        assert g.mask[0] | g.mask[1] | g.mask[2] == (1 << g.lbits) - 1
         assert g.mask[0] & g.mask[1] == 0 and g.mask[1] & g.mask[2] == 0 and g.mask[0] & g.mask[2] == 0
         assert g.thr_in < g.thr < g.thr_out
 
