@@ -108,3 +108,14 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "sph_oracle" not in text, f
+
+
+def test_fails_loudly_without_extension_or_gpu(lib, monkeypatch):
+    """No CPU fallback: a missing library or a non-CUDA device is an error, never a silent detour."""
+    from pyticles_b200 import _lib, backend
+    with pytest.raises(_lib.SphError):
+        backend.NeighbourBackend("cpu")
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", os.path.join(ROOT, "pyticles_b200", "does_not_exist.so"))
+    with pytest.raises(_lib.SphError):
+        _lib.load()
