@@ -188,19 +188,22 @@ class SlabSphEvaluator(object):
         self.n_local = self.n_owned
 
     # ------------------------------------------------------------------ storage
-    def _reserve(self, cap):
-        if cap <= self.cap:
+    def _reserve(self, cap, S=None):
+        S = self.S if S is None else S
+        have = S["m"].shape[0] if "m" in S else 0
+        if cap <= have:
             return
         cap = int(cap * 1.06) + 4096
         shapes = dict(r=(cap, 3), v=(cap, 3), m=(cap,), h=(cap,), t=(cap,), gid=(cap,), rho=(cap,), p=(cap,),
                       pco=(cap,), u=(cap,), vdot=(cap, 3), udot=(cap,))
         for k, shp in shapes.items():
             new = torch.zeros(shp, dtype=torch.int64 if k == "gid" else torch.float64, device=self.device)
-            old = self.S.get(k)
+            old = S.get(k)
             if old is not None:
                 new[:old.shape[0]] = old
-            self.S[k] = new
-        self.cap = cap
+            S[k] = new
+        if S is self.S:
+            self.cap = cap
 
     def _load_rows(self, rows):
         n = rows.shape[0]
@@ -213,8 +216,8 @@ class SlabSphEvaluator(object):
         S["gid"][:n] = rows[:, C_GID].to(torch.int64)
         self.n_owned = int(n)
 
-    def _pack(self, idx):
-        S = self.S
+    def _pack(self, idx, S=None):
+        S = self.S if S is None else S
         return make_rows(S["r"][idx], S["v"][idx], S["m"][idx], S["h"][idx], S["t"][idx], S["gid"][idx])
 
     def rows(self):
@@ -234,30 +237,31 @@ class SlabSphEvaluator(object):
         return self.be.K
 
     # ------------------------------------------------------------------ one evaluation
-    def _halo_a(self):
-        dec, S, no = self.dec, self.S, self.n_owned
+    def _halo_a(self, S):
+        dec, no = self.dec, self.n_owned
         if dec.world == 1:
             dec._halo = None
             return 0
         idx, dest = dec.halo_select_x(S["r"][:no, 0])
-        ghosts, pattern = dec._exchange(self._pack(idx), dest)
+        ghosts, pattern = dec._exchange(self._pack(idx, S), dest)
         dec._halo = (idx, pattern)
         ng = int(ghosts.shape[0])
-        self._reserve(no + ng)
-        S = self.S
+        self._reserve(no + ng, S)
         S["r"][no:no + ng], S["v"][no:no + ng] = ghosts[:, C_R:C_R + 3], ghosts[:, C_V:C_V + 3]
         S["m"][no:no + ng], S["h"][no:no + ng], S["t"][no:no + ng] = ghosts[:, C_M], ghosts[:, C_H], ghosts[:, C_T]
         S["gid"][no:no + ng] = ghosts[:, C_GID].to(torch.int64)
         return ng
 
-    def evaluate(self, timed=False):
+    def evaluate(self, timed=False, S=None):
+        """One distributed derivative evaluation on the storage slot S (default: the primary one)."""
         dec, be = self.dec, self.be
+        S = self.S if S is None else S
         ev = None
         if timed:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
             ev[0].record()
-        ng = self._halo_a()                                   # A
-        S, no = self.S, self.n_owned
+        ng = self._halo_a(S)                                  # A
+        no = self.n_owned
         n = no + ng
         r, v, m, h, t = (S[k][:n] for k in self.IN)
         rho, p, pco, u, vdot, udot = (S[k][:n] for k in self.OUT)
@@ -336,38 +340,70 @@ class SlabSphEvaluator(object):
         return torch.stack([lo[order], hi[order]], dim=1)
 
     def run_e2e(self, steps, warmup):
-        """Every step: pinned-host r, v, m, h, t of the owned particles -> device; evaluate;
-        rho, p, vdot, udot -> pinned host."""
+        """Host-buffer path: every step copies that step's r, v, m, h, t of the owned particles from
+        pinned host memory, evaluates (halo exchanges included), and copies rho, p, vdot, udot back.
+        Frames are independent, so copy-in of frame k+1 and copy-out of frame k-1 overlap the kernels
+        of frame k (two storage slots, three streams) -- as stepper.SphEvaluator.run_e2e does."""
         no = self.n_owned
-        ins = [self.S[k][:no] for k in self.IN]
-        h_in = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in ins]
-        outs = [self.S[k][:no] for k in ("rho", "p", "vdot", "udot")]
-        h_out = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in outs]
-        h2d = sum(t.numel() * t.element_size() for t in ins)
-        d2h = sum(t.numel() * t.element_size() for t in outs)
+        S2 = {}
+        self._reserve(self.S["m"].shape[0], S2)
+        S2["gid"][:no] = self.S["gid"][:no]
+        slots = [self.S, S2]
+        h_in = {k: torch.empty(self.S[k][:no].shape, dtype=torch.float64, pin_memory=True).copy_(self.S[k][:no])
+                for k in self.IN}
+        outs = ("rho", "p", "vdot", "udot")
+        h_out = {k: torch.empty(self.S[k][:no].shape, dtype=torch.float64, pin_memory=True) for k in outs}
+        h2d = sum(t.numel() * t.element_size() for t in h_in.values())
+        d2h = sum(t.numel() * t.element_size() for t in h_out.values())
+        s_comp = torch.cuda.current_stream()
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        comp_done, out_done = [None, None], [None, None]
 
-        def one():
-            for d, hh in zip(ins, h_in):
-                d.copy_(hh, non_blocking=True)
-            self.evaluate()
-            for d, hh in zip(outs, h_out):
-                hh.copy_(d, non_blocking=True)
+        def frame(k):
+            S = slots[k % 2]
+            with torch.cuda.stream(s_in):
+                if comp_done[k % 2] is not None:
+                    s_in.wait_event(comp_done[k % 2])
+                for name in self.IN:
+                    S[name][:no].copy_(h_in[name], non_blocking=True)
+                in_done = torch.cuda.Event()
+                in_done.record(s_in)
+            s_comp.wait_event(in_done)
+            if out_done[k % 2] is not None:
+                s_comp.wait_event(out_done[k % 2])
+            self.evaluate(S=S)
+            S = slots[k % 2]                                   # (evaluate may have regrown the slot)
+            comp_done[k % 2] = torch.cuda.Event()
+            comp_done[k % 2].record(s_comp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(comp_done[k % 2])
+                for name in outs:
+                    h_out[name].copy_(S[name][:no], non_blocking=True)
+                out_done[k % 2] = torch.cuda.Event()
+                out_done[k % 2].record(s_out)
 
-        for _ in range(warmup):
-            one()
+        for k in range(warmup):
+            frame(k)
         torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            one()
-        e1.record()
+        comp_done[:] = [None, None]
+        out_done[:] = [None, None]
+        if self.dec.world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(s_comp)
+        s_in.wait_event(t0)
+        for k in range(steps):
+            frame(k)
+        s_comp.wait_stream(s_out)
+        s_comp.wait_stream(s_in)
+        t1.record(s_comp)
         torch.cuda.synchronize()
         tot = torch.tensor([h2d, d2h], dtype=torch.int64, device=self.device)
-        dist.all_reduce(tot)
-        return {"ms": e0.elapsed_time(e1), "steps": steps, "h2d": int(tot[0]), "d2h": int(tot[1])}
+        if self.dec.world > 1:
+            dist.all_reduce(tot)
+        return {"ms": t0.elapsed_time(t1), "steps": steps, "h2d": int(tot[0]), "d2h": int(tot[1])}
 
 
 def make_rows(r, v, m, h, t, gid):
