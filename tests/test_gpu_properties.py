@@ -111,3 +111,51 @@ def test_bench_emits_contract_line():
         assert k in d, k
     assert d["value"] > 0 and d["gpu_launches"] > 0 and d["roofline"]["frac"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+
+
+def test_bspana_style_front_end_runs(tmp_path):
+    """run_scripts/bspana.py usage contract on this backend: build, properties,
+    update loop with thermostat, list compression / rebuild, trajectory output."""
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "bspana.py"), "12", "8"], cwd=str(tmp_path),
+                         env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Completed 12 steps" in out.stdout and "nan" not in out.stdout
+    from scipy.io import netcdf_file
+    f = netcdf_file(str(tmp_path / "output.nc"), "r", mmap=False)
+    assert f.variables["position"].shape == (2, 512, 3)
+    f.close()
+
+
+def test_create_particle_thermostat_and_euler():
+    from pyticles_b200 import forces, neighbour_list, particles, properties
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    r, v, box = O.lattice_workload(6, 6, 6, seed=3, jitter=0.2)
+    n = r.shape[0]
+    particles.SPROPS = True
+    try:
+        p = particles.SmoothParticleSystem(n, d=3, maxn=n + 4, xmax=box[0], ymax=box[1], zmax=box[2], hshort=2.0,
+                                           integrator='euler', thermostat=True, thermostat_temp=2.0)
+        p.r[0:n, :] = r
+        p.v[0:n, :] = v
+        nl = neighbour_list.VerletList(p, cutoff=2.0, tolerance=1.0)
+        p.nlists.append(nl)
+        p.nl_default = nl
+        p.forces.append(forces.SpamForce(p, nl))
+        nl.build()
+        nip0 = nl.nip
+        p.create_particle((3.0, 3.0, 3.0))                       # particles.py:171-178: grows n, rebuilds
+        assert p.n == n + 1 and nl.nip > nip0
+        nl.separations()
+        properties.spam_properties(p, nl)
+        r0, v0 = p.r[:p.n].clone(), p.v[:p.n].clone()
+        p.update(0.01)
+        vd = p.vdot[:p.n].clone()
+        # euler (integrator.py:14-41): x += xdot * dt with the derivatives of the START state; update()
+        # evaluates them once before the step (particles.py:479) and the step evaluates them again
+        assert float((p.r[:p.n] - (r0 + 0.01 * v0)).abs().max()) < 1e-13
+        assert float(p.t.mean()) == pytest.approx(2.0, rel=1e-12)  # scaling thermostat (particles.py:450-457)
+        assert bool(torch.isfinite(vd).all())
+    finally:
+        particles.SPROPS = False
