@@ -269,7 +269,8 @@ def main():
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ms = float(tm.item())
     clocks = sampler.stop(t0, t1) if rank == 0 else None
-    sim.check()
+    st = sim.check()
+    tile_fallback = bool(st.flags & 32)     # SPH_F_TILE_FALLBACK: the general neighbour kernel did the pass
     passes = sim.pass_times()           # per-pass mean ms over the timed steps (CUDA events)
     pairs = sim.pairs_per_particle()
 
@@ -320,6 +321,7 @@ def main():
                       "l2": "inputs larger than L2 (no flush)" if n_local * 350 > 3 * 126e6 else "working set near L2 size; no flush",
                       "max_nbrs": sim.max_nbrs},
            "roofline": roof, "gpu_launches": sim.launches_per_eval * args.steps}
+    out["config"]["tile_fallback"] = tile_fallback
     if clocks:
         out["clocks"] = clocks
     if e2e:

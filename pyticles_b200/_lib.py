@@ -15,6 +15,7 @@ SPH_F_OUT_OF_RANGE = 2
 SPH_F_OUT_OF_BOX = 4
 SPH_F_NBR_OVERFLOW = 8
 SPH_F_OUT_OF_SLAB = 16
+SPH_F_TILE_FALLBACK = 32
 
 c_double3 = ctypes.c_double * 3
 c_int3 = ctypes.c_int32 * 3

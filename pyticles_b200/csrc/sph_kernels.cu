@@ -27,155 +27,11 @@
 
 #include "pyticles_b200.h"
 
-#define SPH_PI 3.14159265358979323846
+#include "sph_device.cuh"
+#include "sph_tiles.cuh"
 
 namespace {
 
-constexpr int kBlock = 256;
-constexpr int kNlWarps = 8;          // warps per block in the neighbour pass
-constexpr int kNlWin = 512;          // candidates staged per warp per window
-
-struct __align__(16) d2 { double x, y; };
-
-// One 256-bit load (LDG.E.ENL2.256) of a 32-byte-aligned row of four doubles: a gathered row
-// costs one L1 request instead of two 128-bit ones -- the L1 data pipe is what bounds the
-// density and force passes (profiles/r1a_kernels.txt).
-__device__ __forceinline__ void load4(const double *p, double &a, double &b, double &c, double &d)
-{
-    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-}
-
-__device__ __forceinline__ void store4(double *p, double a, double b, double c, double d)
-{
-    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
-}
-
-__device__ __forceinline__ uint32_t pdep32(uint32_t v, uint32_t mask)
-{
-    uint32_t r = 0;
-    while (mask) {
-        const uint32_t low = mask & (0u - mask);
-        if (v & 1u) r |= low;
-        v >>= 1;
-        mask ^= low;
-    }
-    return r;
-}
-
-__device__ __forceinline__ uint32_t pext32(uint32_t v, uint32_t mask)
-{
-    uint32_t r = 0, bit = 1;
-    while (mask) {
-        const uint32_t low = mask & (0u - mask);
-        if (v & low) r |= bit;
-        bit <<= 1;
-        mask ^= low;
-    }
-    return r;
-}
-
-// neighbour_list.py:111-122 -- one shift, strict comparisons against L/2.
-__device__ __forceinline__ double min_image(double d, double L, double half)
-{
-    if (d > half) d = __dsub_rn(d, L);
-    if (d < -half) d = __dadd_rn(d, L);
-    return d;
-}
-
-// rsq exactly as numpy forms it: (dx*dx + dy*dy) + dz*dz, every operation rounded.
-__device__ __forceinline__ double rsq_exact(double dx, double dy, double dz)
-{
-    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-}
-
-// The reference's pair predicate on the reference's operands (neighbour_list.py:170-178).
-__device__ __forceinline__ bool pair_exact(const sph_grid &g, const double *pos4, int a, int j)
-{
-    double ax, ay, az, am, bx, by, bz, bm;
-    load4(pos4 + 4 * (size_t)a, ax, ay, az, am);
-    load4(pos4 + 4 * (size_t)j, bx, by, bz, bm);
-    const double dx = min_image(__dsub_rn(bx, ax), g.box[0], g.box[0] / 2.);
-    const double dy = min_image(__dsub_rn(by, ay), g.box[1], g.box[1] / 2.);
-    const double dz = min_image(__dsub_rn(bz, az), g.box[2], g.box[2] / 2.);
-    return rsq_exact(dx, dy, dz) < g.thr;
-}
-
-// ------------------------------------------------------------------ binning
-struct CellLoc {
-    uint32_t code;
-    float rx, ry, rz;
-    uint32_t flags;
-    bool interior;       // every dimension: >= 5 layers and not the first or last GLOBAL layer
-};
-
-// Cell code = (block index << lbits) | Morton code inside the block.  Blocks are 2^lb x 2^lb x 2^lb
-// cells (lb <= 3) numbered row-major, so the code space exceeds the real cell count by a few per
-// cent only, whatever the number of layers; inside a block the order is a (generalised) Morton curve.
-__device__ __forceinline__ uint32_t cell_code(const sph_grid &g, int cx, int cy, int cz)
-{
-    const uint32_t lx = g.lb[0], ly = g.lb[1], lz = g.lb[2];
-    const uint32_t blk = (((uint32_t)cz >> lz) * g.nblk[1] + ((uint32_t)cy >> ly)) * g.nblk[0] + ((uint32_t)cx >> lx);
-    const uint32_t loc = pdep32((uint32_t)cx & ((1u << lx) - 1u), g.mask[0]) |
-                         pdep32((uint32_t)cy & ((1u << ly) - 1u), g.mask[1]) |
-                         pdep32((uint32_t)cz & ((1u << lz) - 1u), g.mask[2]);
-    return (blk << g.lbits) | loc;
-}
-
-// blk -> (bx, by, bz) with multiply-high division: magic = ceil(2^32 / nblk) is exact here because
-// blk * nblk < 2^31 (sph_grid_plan rejects larger code spaces).
-__device__ __forceinline__ void block_coords(const sph_grid &g, uint32_t blk, uint32_t &bx, uint32_t &by, uint32_t &bz)
-{
-    const uint32_t t = g.nblk[0] == 1u ? blk : __umulhi(blk, g.magic0);
-    bx = blk - t * g.nblk[0];
-    bz = g.nblk[1] == 1u ? t : __umulhi(t, g.magic1);
-    by = t - bz * g.nblk[1];
-}
-
-__device__ __forceinline__ void cell_coords(const sph_grid &g, uint32_t code, int &cx, int &cy, int &cz)
-{
-    uint32_t bx, by, bz;
-    block_coords(g, code >> g.lbits, bx, by, bz);
-    cx = (int)((bx << g.lb[0]) | pext32(code, g.mask[0]));
-    cy = (int)((by << g.lb[1]) | pext32(code, g.mask[1]));
-    cz = (int)((bz << g.lb[2]) | pext32(code, g.mask[2]));
-}
-
-__device__ __forceinline__ int cell_coord(const sph_grid &g, int d, double x, float &rel, uint32_t &flags)
-{
-    const double L = g.box[d];
-    if (!(x >= 0.0 && x < L)) {
-        flags |= SPH_F_OUT_OF_BOX;
-        if (!(x >= -0.25 * L && x <= 1.25 * L)) flags |= SPH_F_OUT_OF_RANGE;
-        if (!(fabs(x) <= 1.0e300)) flags |= SPH_F_NONFINITE;
-    }
-    double f = floor(x * g.inv_w[d]);
-    if (!(fabs(f) < 4.0e15)) f = 0.0;                 // NaN / absurd: any cell, exact path decides
-    const long long cu = (long long)f;
-    rel = (float)(x - (double)cu * g.w[d]);
-    long long cg = cu % g.nc[d];
-    if (cg < 0) cg += g.nc[d];
-    int cl = (int)cg - g.lo[d];
-    if (cl < 0) cl += g.nc[d];
-    if (cl >= g.ncl[d]) { flags |= SPH_F_OUT_OF_SLAB; cl = g.ncl[d] - 1; }
-    return cl;
-}
-
-__device__ __forceinline__ CellLoc locate(const sph_grid &g, double x, double y, double z)
-{
-    CellLoc c;
-    c.flags = 0;
-    const int cc[3] = {cell_coord(g, 0, x, c.rx, c.flags), cell_coord(g, 1, y, c.ry, c.flags),
-                       cell_coord(g, 2, z, c.rz, c.flags)};
-    c.code = cell_code(g, cc[0], cc[1], cc[2]);
-    c.interior = true;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        int cg = cc[d] + g.lo[d];
-        if (cg >= g.nc[d]) cg -= g.nc[d];
-        c.interior = c.interior && g.nc[d] >= 5 && cg >= 1 && cg <= g.nc[d] - 2;
-    }
-    return c;
-}
 
 __global__ void __launch_bounds__(kBlock)
 bin_kernel(const __grid_constant__ sph_grid g, const double *__restrict__ r, int n,
@@ -341,9 +197,11 @@ __global__ void __launch_bounds__(kNlWarps * 32)
 nlist_kernel(const __grid_constant__ sph_grid g, int n, int K,
              const uint32_t *__restrict__ cell_start, const float *__restrict__ rel4,
              const double *__restrict__ pos4, int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
-             sph_status *__restrict__ status)
+             sph_status *__restrict__ status, int only_fallback)
 {
     extern __shared__ float4 smem_cand[];
+    // behind the tile kernels this pass only runs when they gave up (sph_tiles.cu)
+    if (only_fallback && !(status->flags & SPH_F_TILE_FALLBACK)) return;
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     float4 *S = smem_cand + wib * kNlWin;
@@ -553,11 +411,6 @@ struct Interior {
 __device__ __forceinline__ bool cell_is_interior(const sph_grid &, uint32_t flag)
 {
     return flag != 0u;       // computed once per particle by gather_kernel (rel4[., 3])
-}
-
-__device__ __forceinline__ double lucy_norm3(double h)
-{
-    return 105. / (SPH_PI * 16. * (h * h * h));       // spkernel.py:99
 }
 
 constexpr int kRowU = 4;             // neighbours gathered per pipeline stage
@@ -1058,6 +911,11 @@ __global__ void status_reset_kernel(sph_status *status)
     if (threadIdx.x < sizeof(sph_status) / 4) reinterpret_cast<uint32_t *>(status)[threadIdx.x] = 0u;
 }
 
+__global__ void flags_clear_kernel(sph_status *status, uint32_t bits)
+{
+    status->flags &= ~bits;
+}
+
 __global__ void __launch_bounds__(kBlock)
 axpy_kernel(double *__restrict__ x, const double *__restrict__ a, const double *__restrict__ b,
             double s, int64_t len)
@@ -1158,7 +1016,7 @@ int sm_count()
 // ====================================================================== C ABI
 extern "C" {
 
-const char *sph_version(void) { return "pyticles_b200 0.1 (sm_100a, abi 1)"; }
+const char *sph_version(void) { return "pyticles_b200 0.2 (sm_100a, abi 2)"; }
 
 int64_t sph_scan_tmp_elems(uint32_t ncode)
 {
@@ -1341,11 +1199,8 @@ int sph_gather(const sph_grid *g, const sph_buffers *b, const double *d_r, const
     return launch_status();
 }
 
-int sph_nlist_build(const sph_grid *g, const sph_buffers *b, void *stream)
+static int nlist_general(const sph_grid *g, const sph_buffers *b, int only_fallback, cudaStream_t s)
 {
-    if (!g || !b || !b->nbr || !b->cnt || !b->rel4 || !b->pos4 || !b->cell_start || !b->status) return SPH_E_BADARG;
-    if (b->max_nbrs <= 0) return SPH_E_BADARG;
-    if (b->n == 0) return SPH_OK;
     static bool configured = false;
     const size_t smem = sizeof(float4) * kNlWin * kNlWarps;
     if (!configured) {
@@ -1359,12 +1214,28 @@ int sph_nlist_build(const sph_grid *g, const sph_buffers *b, void *stream)
     const int64_t cap = (int64_t)sm_count() * 3 * 8;       // a few resident waves, grid-stride beyond
     if (blocks > cap) blocks = cap;
     if (small)
-        nlist_kernel<true><<<(unsigned)blocks, kNlWarps * 32, smem, (cudaStream_t)stream>>>(
-            *g, b->n, b->max_nbrs, b->cell_start, b->rel4, b->pos4, b->nbr, b->cnt, b->status);
+        nlist_kernel<true><<<(unsigned)blocks, kNlWarps * 32, smem, s>>>(
+            *g, b->n, b->max_nbrs, b->cell_start, b->rel4, b->pos4, b->nbr, b->cnt, b->status, only_fallback);
     else
-        nlist_kernel<false><<<(unsigned)blocks, kNlWarps * 32, smem, (cudaStream_t)stream>>>(
-            *g, b->n, b->max_nbrs, b->cell_start, b->rel4, b->pos4, b->nbr, b->cnt, b->status);
+        nlist_kernel<false><<<(unsigned)blocks, kNlWarps * 32, smem, s>>>(
+            *g, b->n, b->max_nbrs, b->cell_start, b->rel4, b->pos4, b->nbr, b->cnt, b->status, only_fallback);
     return launch_status();
+}
+
+int sph_nlist_build(const sph_grid *g, const sph_buffers *b, void *stream)
+{
+    if (!g || !b || !b->nbr || !b->cnt || !b->rel4 || !b->pos4 || !b->cell_start || !b->status) return SPH_E_BADARG;
+    if (b->max_nbrs <= 0) return SPH_E_BADARG;
+    if (b->n == 0) return SPH_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    // the cell-group kernel first; the general kernel behind it returns at once unless that one gave up
+    const bool tiles = sph_tiles::eligible(g, b);
+    if (tiles) {
+        flags_clear_kernel<<<1, 1, 0, s>>>(b->status, SPH_F_TILE_FALLBACK);
+        const int rc = sph_tiles::launch_list(g, b, s);
+        if (rc != SPH_OK) return rc;
+    }
+    return nlist_general(g, b, tiles ? 1 : 0, s);
 }
 
 int sph_density_eos(const sph_grid *g, const sph_buffers *b, const sph_eos *eos,
@@ -1405,6 +1276,7 @@ int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, co
         pressure_term_kernel<<<nb, kBlock, 0, s>>>(b->n, 0, b->perm, d_press, d_rho, b->vel4);
     const double fcutsq = fcutoff * fcutoff;                // forces.py:36
     const int lpp = lanes_per_particle();
+
 #define SPH_LAUNCH_FORCE(U, L)                                                                                 \
     force_kernel<U, L><<<blocks_for((int64_t)b->n * L, kBlock), kBlock, 0, s>>>(                               \
         *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig,        \

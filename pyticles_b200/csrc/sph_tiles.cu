@@ -1,0 +1,374 @@
+// pyticles_b200 -- cell-group ("tile") neighbour pass for sm_100a.
+//
+// One block works on a GROUP of 2 x 2 x 2 cells (eight consecutive block-Morton codes), one warp
+// per cell.  The block stages the 4 x 4 x 4 cells around the group ONCE in shared memory as fp32
+// positions in the group's frame, so a particle row is read from L2 8x instead of 27x, with
+// coalesced loads.
+//
+// Inside a warp, lane = q * P + p: particle p of the cell (P particles) and candidate stream q of
+// Q = 32 / P.  A lane walks every Q-th candidate of the 9 window columns (3 cells each, contiguous
+// in the staged window) around its cell and keeps its own list of hits -- no ballot, no popc, one
+// predicated shared store per hit; 14 instructions per 32 tests against 26 in the warp-per-cell
+// kernel of sph_kernels.cu.  The Q lists of a particle are then concatenated, in a fixed order,
+// into its warp-transposed ELL row (the neighbour structure every other pass and the export use).
+//
+// Exactness is the one of the general kernel: rsq32 < thr_in accepts, rsq32 >= thr_out rejects,
+// hits inside the fp32 error band are decided by the reference's fp64 predicate (pair_exact).
+// Cases outside the fixed capacities (> 32 particles in a cell, > 64 hits in a lane's list,
+// > 1024 particles in the 64 cells of a window, positions far outside the box) raise
+// SPH_F_TILE_FALLBACK and the general kernel redoes the pass.
+//
+// Reference semantics (file:line into the reference tree):
+//   pair predicate     neighbour_list.py:105-123,170-178
+#include <stdlib.h>
+
+#include "sph_device.cuh"
+#include "sph_tiles.cuh"
+
+namespace {
+
+constexpr int kTWarps = 8;           // warps per block = cells per group
+constexpr int kTThreads = kTWarps * 32;
+constexpr int kTCap = 1024;          // staged candidates per group (64 cells)
+constexpr int kTRow = 64;            // hits one lane can hold
+constexpr int kTRowS = 66;           // list stride in shared memory (entries; 33 words: lanes fall in distinct banks)
+constexpr int kTPart = 32;           // particles per cell the tile path handles (cell width ~2 lattice planes: 8 .. 27)
+constexpr int kTQMax = 8;            // candidate streams per particle at most
+
+constexpr uint32_t kFull = 0xffffffffu;
+
+struct TileArgs {
+    int n, K;
+    const uint32_t *cell_start;
+    const float *rel4;
+    const double *pos4;
+    int32_t *nbr;
+    int32_t *cnt;
+    sph_status *status;
+    float thr_in, thr_out;
+};
+
+// shared memory of a block: [S32 | B | Head]
+struct Head {
+    uint32_t off[68];        // exclusive scan of cnt (65 used)
+    uint32_t start[64];      // first sorted particle of window cell (wz*4 + wy)*4 + wx
+    uint32_t cnt[64];
+    float shift[12];         // (i - 1) * w[d] at [4 d + i]: fp32 frame shift of window layer i
+    int gc[4];               // local cell coordinates of the group's base cell
+};
+
+constexpr size_t kBytesS32 = sizeof(float4) * kTCap;
+constexpr size_t kBytesB = sizeof(uint16_t) * kTWarps * 32 * kTRowS;
+constexpr size_t kSmemList = kBytesS32 + kBytesB + sizeof(Head);
+static_assert(4 * (kSmemList + 1024) <= 227 * 1024, "four blocks per SM");
+static_assert(kBytesS32 + 1024 < 65536, "hits are kept as 16-bit shared addresses of the staged candidate");
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ------------------------------------------------------------------ window of a group
+// Fills Head (window cells, their scan, frame shifts, base coordinates) and stages the window:
+// S32 = fp32 position in the group's frame + sorted index.  Returns the number of staged
+// candidates (> kTCap: nothing was staged).
+__device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, const TileArgs &a, Head *H,
+                                               float4 *S32)
+{
+    const int t = threadIdx.x;
+    if (t < 64) {
+        int cc[3];
+        cell_coords(g, c0, cc[0], cc[1], cc[2]);
+        if (t < 3) H->gc[t] = cc[t];
+        if (t < 12) H->shift[t] = (float)((double)((t & 3) - 1) * g.w[t >> 2]);
+        const int o[3] = {(t & 3) - 1, ((t >> 2) & 3) - 1, (t >> 4) - 1};
+        bool ok = true;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            cc[d] += o[d];
+            if (cc[d] < 0) {
+                if (g.wrap[d]) cc[d] += g.ncl[d]; else ok = false;
+            } else if (cc[d] >= g.ncl[d]) {
+                if (g.wrap[d]) cc[d] -= g.ncl[d]; else ok = false;
+            }
+        }
+        uint32_t st = 0, cn = 0;
+        if (ok) {
+            const uint32_t code = cell_code(g, cc[0], cc[1], cc[2]);
+            st = a.cell_start[code];
+            cn = a.cell_start[code + 1] - st;
+        }
+        H->start[t] = st;
+        H->cnt[t] = cn;
+    }
+    __syncthreads();
+    if (t < 32) {
+        const uint32_t v0 = H->cnt[2 * t], v1 = H->cnt[2 * t + 1];
+        uint32_t inc = v0 + v1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t x = __shfl_up_sync(kFull, inc, o);
+            if (t >= o) inc += x;
+        }
+        const uint32_t ex = inc - (v0 + v1);
+        H->off[2 * t] = ex;
+        H->off[2 * t + 1] = ex + v0;
+        if (t == 31) H->off[64] = inc;
+    }
+    __syncthreads();
+    const uint32_t total = H->off[64];
+    if (total > (uint32_t)kTCap) return total;
+    // warp w stages window cells 8w .. 8w+7, four cells per pass (8 lanes each)
+    const int w = t >> 5, lane = t & 31;
+    const float4 *rel = reinterpret_cast<const float4 *>(a.rel4);
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int wc = w * 8 + pass * 4 + (lane >> 3);
+        const uint32_t st = H->start[wc], cn = H->cnt[wc], dst = H->off[wc];
+        const float fx = H->shift[wc & 3], fy = H->shift[4 + ((wc >> 2) & 3)], fz = H->shift[8 + (wc >> 4)];
+        for (uint32_t k = lane & 7; k < cn; k += 8) {
+            const float4 p = __ldg(rel + st + k);
+            S32[dst + k] = make_float4(p.x + fx, p.y + fy, p.z + fz, __int_as_float((int)(st + k)));
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
+// One warp = one home cell of the group.  lane = q * P + p: particle p (of P), candidate stream q (of Q).
+struct Home {
+    int P, Q, lgq, p, q;
+    bool active;             // q < Q
+    uint32_t cs;             // first sorted particle of the cell
+    uint32_t selfc;          // window index of particle p
+    int hx, hy, hz;
+};
+
+__device__ __forceinline__ Home home_of(const sph_grid &g, const Head *H, int w, int lane)
+{
+    Home h;
+    h.hx = w & 1; h.hy = (w >> 1) & 1; h.hz = w >> 2;
+    const int wc = ((1 + h.hz) * 4 + (1 + h.hy)) * 4 + (1 + h.hx);
+    // the last group of an odd layer count is half empty: its window cell is the periodic image of layer 0
+    const bool exists = H->gc[0] + h.hx < g.ncl[0] && H->gc[1] + h.hy < g.ncl[1] && H->gc[2] + h.hz < g.ncl[2];
+    h.P = exists ? (int)H->cnt[wc] : 0;
+    h.cs = H->start[wc];
+    const int P = h.P > 0 ? h.P : 1;
+    h.Q = P <= 4 ? kTQMax : 32 / P;
+    h.lgq = 31 - __clz(h.Q);
+    h.q = (int)(((float)lane + 0.5f) * __frcp_rn((float)P));     // lane / P: never within 1/64 of an integer
+    h.p = lane - h.q * P;
+    h.active = h.q < h.Q;
+    h.selfc = H->off[wc] + (uint32_t)h.p;
+    return h;
+}
+
+// One candidate stream of one window column against one home particle, two candidates per trip.
+// A hit (rsq32 < thr_out) is kept as the 16-bit shared address of the staged candidate; the band
+// [thr_in, thr_out) is settled by the caller from `maxacc`.  SELF: the column holds the particle itself.
+template <bool CHECK, bool SELF>
+__device__ __forceinline__ void test_one(uint32_t ptr, uint32_t selfptr, const float4 &hp, float thr_out,
+                                         float cx, float cy, float cz, uint32_t &lp, uint32_t lp_lim,
+                                         float &maxacc, bool &over)
+{
+    const float dx = cx - hp.x, dy = cy - hp.y, dz = cz - hp.z;
+    const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    if (rsq < thr_out && (!SELF || ptr != selfptr)) {
+        if (CHECK && lp >= lp_lim) {
+            over = true;
+        } else {
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(lp), "h"((unsigned short)ptr) : "memory");
+            lp += 2u;
+            maxacc = fmaxf(maxacc, rsq);
+        }
+    }
+}
+
+template <bool CHECK, bool SELF>
+__device__ __forceinline__ void test_column(uint32_t ptr, uint32_t pend, uint32_t step, uint32_t selfptr,
+                                            const float4 &hp, float thr_out, uint32_t &lp, uint32_t lp_lim,
+                                            float &maxacc, bool &over)
+{
+    float ax, ay, az, aw, bx, by, bz, bw;
+    for (; ptr + step < pend; ptr += 2u * step) {
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ax), "=f"(ay), "=f"(az), "=f"(aw) : "r"(ptr));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bx), "=f"(by), "=f"(bz), "=f"(bw) : "r"(ptr + step));
+        test_one<CHECK, SELF>(ptr, selfptr, hp, thr_out, ax, ay, az, lp, lp_lim, maxacc, over);
+        test_one<CHECK, SELF>(ptr + step, selfptr, hp, thr_out, bx, by, bz, lp, lp_lim, maxacc, over);
+    }
+    if (ptr < pend) {
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ax), "=f"(ay), "=f"(az), "=f"(aw) : "r"(ptr));
+        test_one<CHECK, SELF>(ptr, selfptr, hp, thr_out, ax, ay, az, lp, lp_lim, maxacc, over);
+    }
+}
+
+// ------------------------------------------------------------------ neighbour kernel
+__global__ void __launch_bounds__(kTThreads, 4)
+tile_list_kernel(const __grid_constant__ sph_grid g, const __grid_constant__ TileArgs a)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4 *S32 = reinterpret_cast<float4 *>(smem);
+    uint16_t *Ball = reinterpret_cast<uint16_t *>(smem + kBytesS32);
+    Head *H = reinterpret_cast<Head *>(smem + kBytesS32 + kBytesB);
+
+    // positions far outside the box: single-shift semantics matter, the general path decides
+    if ((a.status->flags & (SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE)) || smem_u32(S32) + kBytesS32 > 65536u) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
+        return;
+    }
+    const uint32_t c0 = blockIdx.x * 8u;
+    if (a.cell_start[c0 + 8] == a.cell_start[c0]) return;                // no particle in the group
+
+    const uint32_t total = tile_stage(g, c0, a, H, S32);
+    if (total > (uint32_t)kTCap) {
+        if (threadIdx.x == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
+        return;
+    }
+
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const Home hm = home_of(g, H, w, lane);
+    const int P = hm.P;
+    if (P == 0) return;
+    if (P > kTPart) {
+        if (lane == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
+        return;
+    }
+    const uint32_t asorted = hm.cs + (uint32_t)hm.p;
+    uint16_t *B = Ball + (w * 32 + lane) * kTRowS;                       // this lane's list of hits
+
+    const uint32_t s32a = smem_u32(S32);
+    const uint32_t selfptr = s32a + hm.selfc * 16u;
+    const float4 hp = S32[hm.selfc];
+    const uint32_t lp0 = smem_u32(B), lp_lim = lp0 + 2u * kTRow;
+    uint32_t lp = lp0;
+    float maxacc = 0.f;
+    bool over = false;
+    if (hm.active) {
+        const uint32_t step = (uint32_t)hm.Q * 16u;
+        const uint32_t *offh = H->off + (hm.hz * 4 + hm.hy) * 4 + hm.hx;
+#pragma unroll
+        for (int col = 0; col < 9; ++col) {
+            const uint32_t s = offh[((col / 3) * 4 + col % 3) * 4], e = offh[((col / 3) * 4 + col % 3) * 4 + 3];
+            const uint32_t pend = s32a + e * 16u, pbeg = s32a + (s + (uint32_t)hm.q) * 16u;
+            // this lane tests at most ((e - s) >> lgq) + 1 candidates of the column: with room for that
+            // many hits the loop needs no capacity test
+            const bool room = lp + 2u * (((e - s) >> hm.lgq) + 1u) <= lp_lim;
+            if (col == 4) {                                              // resolved by the unrolling
+                if (room) test_column<false, true>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
+                else test_column<true, true>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
+            } else {
+                if (room) test_column<false, false>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
+                else test_column<true, false>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
+            }
+        }
+    }
+    if (__any_sync(kFull, over)) {
+        if (lane == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
+        return;
+    }
+    const uint32_t s16 = s32a & 0xffffu;
+    // rare: some hit of this lane lies in the fp32 error band -> the reference's fp64 predicate on all of them
+    if (maxacc >= a.thr_in) {
+        const int nl = (int)((lp - lp0) >> 1);
+        int m = 0;
+        for (int k = 0; k < nl; ++k) {
+            const uint16_t raw = B[k];
+            const int j = __float_as_int(S32[(((uint32_t)raw - s16) & 0xffffu) >> 4].w);
+            if (pair_exact(g, a.pos4, (int)asorted, j)) B[m++] = raw;
+        }
+        lp = lp0 + 2u * (uint32_t)m;
+    }
+    const int cntl = (int)((lp - lp0) >> 1);
+    // concatenate the Q lists of a particle: offsets by a fixed-order walk over the streams
+    int offq = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < kTQMax; ++k) {
+        const int v = __shfl_sync(kFull, cntl, (k * P + hm.p) & 31);
+        if (k < hm.Q) {
+            if (k < hm.q) offq += v;
+            tot += v;
+        }
+    }
+    if (hm.active) {
+        int32_t *erow = a.nbr + ((size_t)(asorted >> 5) * (size_t)a.K + (size_t)offq) * 32 + (asorted & 31);
+        const int nw = min(cntl, a.K - offq);                            // entries beyond the capacity are dropped
+        for (int k = 0; k < nw; ++k) {
+            const uint32_t c16 = ((uint32_t)B[k] - s16) & 0xfff0u;       // 16 * window index
+            erow[(size_t)k * 32] = __float_as_int(*reinterpret_cast<const float *>(
+                reinterpret_cast<const unsigned char *>(S32) + c16 + 12));
+        }
+        if (hm.q == 0) a.cnt[asorted] = tot;
+    } else {
+        tot = 0;
+    }
+    const uint32_t wmax = __reduce_max_sync(kFull, (uint32_t)tot);
+    if (lane == 0) {
+        if (wmax > *(volatile uint32_t *)&a.status->max_count) atomicMax(&a.status->max_count, wmax);
+        if (wmax > (uint32_t)a.K) atomicOr(&a.status->flags, SPH_F_NBR_OVERFLOW);
+    }
+}
+
+void tile_thresholds(const sph_grid *g, float *tin, float *tout)
+{
+    // Positions are fp32 in the GROUP's frame: |coordinate| < 3 w, so a staged coordinate carries
+    // at most 6u w (cell-relative conversion, shift conversion, their sum), the home particle's
+    // 4u w, the subtraction another u w near the threshold: 12u w per component is a bound.  rsq
+    // inherits 2 sqrt(3) r err + 3 err^2 plus ~3u relative from its own arithmetic; use 4x, as
+    // sph_grid_plan does for the per-cell frame.
+    double wmax = 0.0;
+    for (int d = 0; d < 3; ++d) wmax = g->w[d] > wmax ? g->w[d] : wmax;
+    const double u = 1.0 / 16777216.0;
+    const double rl = sqrt(g->thr);
+    const double err = 12.0 * u * wmax;
+    const double band = 4.0 * (2.0 * 1.7320508 * (rl + err) * err + 3.0 * err * err + 8.0 * u * g->thr);
+    float a = (float)(g->thr - band), b = (float)(g->thr + band);
+    a = nextafterf(a, -INFINITY);
+    b = nextafterf(b, INFINITY);
+    if (!(a > 0.0f)) a = 0.0f;
+    *tin = a;
+    *tout = b;
+}
+
+TileArgs base_args(const sph_grid *g, const sph_buffers *b)
+{
+    TileArgs a = {};
+    a.n = b->n;
+    a.K = b->max_nbrs;
+    a.cell_start = b->cell_start;
+    a.rel4 = b->rel4;
+    a.pos4 = b->pos4;
+    a.nbr = b->nbr;
+    a.cnt = b->cnt;
+    a.status = b->status;
+    tile_thresholds(g, &a.thr_in, &a.thr_out);
+    return a;
+}
+
+}  // namespace
+
+namespace sph_tiles {
+
+bool eligible(const sph_grid *g, const sph_buffers *b)
+{
+    const char *e = getenv("SPH_TILES");                 // SPH_TILES=0: general kernel only (tests, A/B timing)
+    if ((e && atoi(e) == 0) || !b->rel4 || !b->pos4 || !b->nbr || !b->cnt) return false;
+    for (int d = 0; d < 3; ++d)
+        if (g->ncl[d] < 3 || g->lb[d] < 1) return false;
+    // the three lowest code bits are one bit of x, y, z: a group of 8 consecutive codes is 2 x 2 x 2 cells
+    return (g->mask[0] & 7u) == 1u && (g->mask[1] & 7u) == 2u && (g->mask[2] & 7u) == 4u && (g->ncode % 8u) == 0u;
+}
+
+int launch_list(const sph_grid *g, const sph_buffers *b, cudaStream_t s)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(tile_list_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList);
+        configured = true;
+    }
+    const TileArgs a = base_args(g, b);
+    tile_list_kernel<<<g->ncode / 8u, kTThreads, kSmemList, s>>>(*g, a);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPH_OK : (int)e;
+}
+
+}  // namespace sph_tiles

@@ -161,7 +161,7 @@ class SlabSphEvaluator(object):
     Owned particles live at the front of persistent structure-of-arrays tensors; the ghosts of
     the current evaluation are appended behind them."""
     kernel_names = {"cells+reorder": "bin_kernel+scan+scatter_kernel+cell_sort_kernel+gather_kernel",
-                    "neighbour": "nlist_kernel", "density": "density_kernel<true>", "force": "force_kernel<true>",
+                    "neighbour": "tile_list_kernel", "density": "density_kernel<true>", "force": "force_kernel<true>",
                     "halo": "slab_select_kernel + all_to_all_single (NCCL)"}
     ncu_traffic = {}
     IN = ("r", "v", "m", "h", "t")
@@ -183,7 +183,7 @@ class SlabSphEvaluator(object):
         vol = box[0] * box[1] * box[2]
         rl = (cutoff * cutoff + tol * tol) ** 0.5
         self.be.user_max_nbrs = int(1.35 * 4.18879 * rl ** 3 * self.n_total / vol) + 16
-        self.launches_per_eval = 13     # the 11 of one GPU + slab_select + pressure_term (ghosts)
+        self.launches_per_eval = 15     # the 13 of one GPU + slab_select + pressure_term (ghosts)
         self._events = []
         self.n_local = self.n_owned
 

@@ -11,15 +11,16 @@ import torch
 from . import _lib, forces, neighbour_list, particles, properties
 from .array import parray
 
-# launches of OUR kernels per evaluation: status_reset, bin, scan x3, scatter, cell_sort,
-# gather, nlist, density, force  (cudaMemset of the cell counters and the two torch fills of
-# vdot/udot are not counted)
-LAUNCHES_PER_EVAL = 11
+# launches of OUR kernels per evaluation: status_reset, bin, scan x3, scatter, cell_sort, gather (8);
+# flags_clear, tile_list, nlist (the general kernel behind the tile kernel: launched, returns at once
+# unless that one gave up) (3); density, force (2).  cudaMemset of the cell counters and the two
+# torch fills of vdot/udot are not counted.
+LAUNCHES_PER_EVAL = 13
 
 
 class SphEvaluator(object):
     kernel_names = {"cells+reorder": "bin_kernel+scan+scatter_kernel+cell_sort_kernel+gather_kernel",
-                    "neighbour": "nlist_kernel", "density": "density_kernel<true>", "force": "force_kernel<true>"}
+                    "neighbour": "tile_list_kernel", "density": "density_kernel<true>", "force": "force_kernel<true>"}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` on the c3 workload
     # (profiles/r1b_kernels.txt, r1c_nlist.txt); only meaningful for that workload
     ncu_traffic = {"cells+reorder": None, "neighbour": 3.03e9, "density": 5.05e9, "force": 4.85e9}

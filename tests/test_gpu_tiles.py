@@ -1,0 +1,175 @@
+"""The cell-group (tile) neighbour kernel against the general kernel and the CPU oracle.
+
+The tile kernel (pyticles_b200/csrc/sph_tiles.cu) is the fast path of the neighbour pass; the
+general warp-per-cell kernel behind it redoes the pass when a fixed capacity is exceeded
+(SPH_F_TILE_FALLBACK).  Both must give the reference's pair set bit-exactly, and the fields computed
+from either structure must agree with the oracle (<= 1e-10) and with each other (rows hold the same
+sets in a different order, so sums differ by rounding only).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as C
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+from test_gpu_parity import _np, check_against, make_system, rel_err, run_step  # noqa: E402
+
+
+class tiles(object):
+    """with tiles(False): the general kernel only (SPH_TILES is read at every call)."""
+
+    def __init__(self, on):
+        self.on = on
+
+    def __enter__(self):
+        self.old = os.environ.get("SPH_TILES")
+        os.environ["SPH_TILES"] = "1" if self.on else "0"
+
+    def __exit__(self, *a):
+        if self.old is None:
+            os.environ.pop("SPH_TILES", None)
+        else:
+            os.environ["SPH_TILES"] = self.old
+
+
+def fallback_flag(nl):
+    from pyticles_b200 import _lib
+    return bool(nl.backend.status().flags & _lib.SPH_F_TILE_FALLBACK)
+
+
+def fields(p, n):
+    return {k: _np(getattr(p, k))[:n].copy() for k in ("rho", "p", "pco", "u", "t", "vdot", "udot")}
+
+
+@pytest.mark.parametrize("shape,cutoff,tol,jitter", [
+    ((32, 32, 32), 2.0, 0.0, 0.1),       # C3-like: 15 layers per dimension, cells of 8 .. 27 particles
+    ((26, 22, 18), 2.0, 0.0, 0.1),       # odd layer counts (13, 11, 9): the periodic seam falls inside a group
+    ((14, 10, 6), 2.0, 0.0, 0.2),        # 7, 5 and 3 layers: every cell is a boundary cell in z
+    ((24, 24, 24), 2.0, 1.0, 0.45),      # heavy jitter, default Verlet tolerance (~47 neighbours)
+    ((128, 128, 1), 2.0, 0.0, 0.1),      # C2-like sheet in a deep box
+    ((20, 20, 20), 1.5, 0.0, 0.3),       # short cutoff: 13 layers of ~3.6 particles, Q = 8 streams
+])
+def test_tile_kernel_matches_oracle_and_general_kernel(shape, cutoff, tol, jitter):
+    r, v, box = O.lattice_workload(*shape, seed=31, jitter=jitter)
+    if shape[2] == 1:
+        box = (box[0], box[1], float(shape[0]))
+    n = r.shape[0]
+    rng = np.random.default_rng(5)
+    m, h, t = rng.uniform(0.8, 1.2, n), np.full(n, 2.0), rng.uniform(0.8, 1.2, n)
+    ref = C.sph_step(r, v, m, h, t, np.array(box), cutoff, tol, 5.0)
+    out = {}
+    for on in (True, False):
+        with tiles(on):
+            p = make_system(r, v, m, h, t, box)
+            nl = run_step(p, cutoff, tol, 5.0)
+            check_against(p, nl, ref, n)
+            assert fallback_flag(nl) is False, "the tile kernel gave up on a case it is meant to handle" if on \
+                else "SPH_TILES=0 must not touch the tile kernel"
+            out[on] = fields(p, n)
+    for k in out[True]:
+        assert rel_err(out[True][k], out[False][k]) < 1e-11, k
+
+
+def test_tile_kernel_rows_hold_the_same_sets():
+    """Row by row: the ELL structure of the tile kernel is a permutation of the general kernel's."""
+    from pyticles_b200 import neighbour_list
+    r, v, box = O.lattice_workload(20, 20, 20, seed=33, jitter=0.3)
+    n = r.shape[0]
+    rows = {}
+    for on in (True, False):
+        with tiles(on):
+            p = make_system(r, v, np.ones(n), np.full(n, 2.0), np.ones(n), box)
+            nl = neighbour_list.VerletList(p, cutoff=2.0, tolerance=0.0)
+            nl.build()
+            be = nl.backend
+            K = be.K
+            nbr = _np(be.t["nbr"])[: ((n + 31) // 32) * 32 * K].reshape(-1, K, 32)
+            cnt = _np(be.t["cnt"])[:n]
+            perm = _np(be.t["perm"])[:n]
+            rows[on] = (nbr.copy(), cnt.copy(), perm.copy())
+    (na, ca, pa), (nb, cb, pb) = rows[True], rows[False]
+    assert np.array_equal(pa, pb) and np.array_equal(ca, cb)
+    for a in range(0, n, 37):
+        ra = np.sort(na[a >> 5, : ca[a], a & 31])
+        rb = np.sort(nb[a >> 5, : cb[a], a & 31])
+        assert np.array_equal(ra, rb), a
+
+
+def test_tile_kernel_is_reproducible():
+    r, v, box = O.lattice_workload(20, 20, 20, seed=33, jitter=0.3)
+    n = r.shape[0]
+    m, h, t = np.ones(n), np.full(n, 2.0), np.ones(n)
+    runs = []
+    for _ in range(2):
+        p = make_system(r, v, m, h, t, box)
+        nl = run_step(p, 2.0, 0.0, 5.0)
+        assert not fallback_flag(nl)
+        runs.append(fields(p, n))
+    for k in runs[0]:
+        assert np.array_equal(runs[0][k], runs[1][k]), k
+
+
+@pytest.mark.parametrize("kind", ["crowded_cell", "crowded_window", "long_lists"])
+def test_capacity_limits_fall_back_to_the_general_kernel(kind):
+    rng = np.random.default_rng(7)
+    r, v, box = O.lattice_workload(12, 12, 12, seed=35, jitter=0.1)
+    if kind == "crowded_cell":          # 40 more particles in one cell (> 32 per cell)
+        extra = np.array([5.0, 5.0, 5.0]) + rng.uniform(0.0, 0.5, size=(40, 3))
+    elif kind == "crowded_window":      # 3.4 particles per unit volume: > 1024 candidates around a group
+        extra = rng.uniform(0.0, 12.0, size=(4200, 3))
+    else:                               # a tight cluster of 30 next to a cell of 8: every lane of that cell lists > 64 / Q hits
+        extra = np.array([3.05, 3.05, 3.05]) + rng.uniform(0.0, 0.9, size=(30, 3))
+    r = np.vstack([r, extra])
+    v = np.vstack([v, rng.uniform(-0.05, 0.05, size=extra.shape)])
+    n = r.shape[0]
+    m, h, t = np.ones(n), np.full(n, 2.0), np.ones(n)
+    ref = C.sph_step(r, v, m, h, t, np.array(box), 2.0, 0.0, 5.0)
+    p = make_system(r, v, m, h, t, box)
+    nl = run_step(p, 2.0, 0.0, 5.0)
+    if kind != "long_lists":
+        assert fallback_flag(nl)
+    check_against(p, nl, ref, n, pair_arrays=False)
+
+
+def test_long_rows_grow_the_ell_capacity_without_fallback():
+    """cutoff 3: ~110 neighbours per particle.  Rows longer than max_nbrs are an ELL overflow (the host
+    grows the capacity and repeats the pass), not a tile-kernel limit."""
+    from pyticles_b200 import neighbour_list
+    r, v, box = O.lattice_workload(15, 15, 15, seed=41, jitter=0.1)
+    n = r.shape[0]
+    p = make_system(r, v, np.ones(n), np.full(n, 2.0), np.ones(n), box)
+    nl = neighbour_list.VerletList(p, cutoff=3.0, tolerance=0.0, max_nbrs=16)
+    nl.build()
+    assert nl.backend.K > 100
+    assert np.array_equal(_np(nl.iap), C.build_pairs(r, np.array(box), 3.0, 0.0))
+
+
+def test_evaluator_against_oracle():
+    """stepper.SphEvaluator (what bench.py times) on the tile kernel, against the oracle."""
+    import torch
+    from pyticles_b200 import _lib, forces, neighbour_list, particles, stepper
+    from pyticles_b200.array import parray
+    r, v, box = O.lattice_workload(32, 32, 32, seed=37, jitter=0.1)
+    n = r.shape[0]
+    ref = C.sph_step(r, v, np.ones(n), np.full(n, 2.0), np.ones(n), np.array(box), 2.0, 0.0, 5.0)
+    p = particles.SmoothParticleSystem(n, d=3, maxn=n, xmax=box[0], ymax=box[1], zmax=box[2], hshort=2.0)
+    p.r = parray(torch.as_tensor(r, device="cuda"))
+    p.v = parray(torch.as_tensor(v, device="cuda"))
+    nl = neighbour_list.VerletList(p, cutoff=2.0, tolerance=0.0)
+    nl.defer_status = True
+    p.nlists.append(nl)
+    p.nl_default = nl
+    f = forces.SpamForce(p, nl, cutoff=5.0)
+    p.forces.append(f)
+    ev = stepper.SphEvaluator(p, nl, f)
+    for _ in range(2):
+        ev.evaluate()
+    st = ev.check()
+    assert not st.flags & _lib.SPH_F_TILE_FALLBACK
+    for name in ("rho", "p", "pco", "u", "vdot", "udot"):
+        assert rel_err(_np(getattr(p, name))[:n], ref[name]) < 1e-10, name
+    assert np.array_equal(_np(nl.backend.export_pairs()).astype(np.int64), ref["iap"].astype(np.int64))
