@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpyticles_b200.so")
+# PYTICLES_B200_LIB selects another build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("PYTICLES_B200_LIB") or os.path.join(HERE, "libpyticles_b200.so")
 
 SPH_OK = 0
 SPH_F_NONFINITE = 1

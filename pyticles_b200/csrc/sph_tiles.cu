@@ -5,17 +5,18 @@
 // positions in the group's frame, so a particle row is read from L2 8x instead of 27x, with
 // coalesced loads.
 //
-// Inside a warp, lane = q * P + p: particle p of the cell (P particles) and candidate stream q of
-// Q = 32 / P.  A lane walks every Q-th candidate of the 9 window columns (3 cells each, contiguous
-// in the staged window) around its cell and keeps its own list of hits -- no ballot, no popc, one
-// predicated shared store per hit; 14 instructions per 32 tests against 26 in the warp-per-cell
-// kernel of sph_kernels.cu.  The Q lists of a particle are then concatenated, in a fixed order,
-// into its warp-transposed ELL row (the neighbour structure every other pass and the export use).
+// A warp takes the particles of its cell up to 16 at a time.  Inside a pass, lane = q * P + p:
+// particle p (of P) and candidate stream q of Q = 32 / P.  A lane walks every Q-th candidate of the
+// 9 window columns (3 cells each, contiguous in the staged window) around its cell and keeps its
+// own list of hits -- no ballot, no popc, one predicated shared store per hit; 14 instructions per
+// 32 tests against 26 in the warp-per-cell kernel of sph_kernels.cu.  The Q lists of a particle are
+// then concatenated, in a fixed order, into its warp-transposed ELL row (the neighbour structure
+// every other pass and the export use).
 //
 // Exactness is the one of the general kernel: rsq32 < thr_in accepts, rsq32 >= thr_out rejects,
 // hits inside the fp32 error band are decided by the reference's fp64 predicate (pair_exact).
-// Cases outside the fixed capacities (> 32 particles in a cell, > 64 hits in a lane's list,
-// > 1024 particles in the 64 cells of a window, positions far outside the box) raise
+// Cases outside the fixed capacities (> 64 particles in a cell, > 32 hits in one stream's list even
+// at Q >= 4, > 1024 particles in the 64 cells of a window, positions far outside the box) raise
 // SPH_F_TILE_FALLBACK and the general kernel redoes the pass.
 //
 // Reference semantics (file:line into the reference tree):
@@ -30,10 +31,13 @@ namespace {
 constexpr int kTWarps = 8;           // warps per block = cells per group
 constexpr int kTThreads = kTWarps * 32;
 constexpr int kTCap = 1024;          // staged candidates per group (64 cells)
-constexpr int kTRow = 64;            // hits one lane can hold
-constexpr int kTRowS = 66;           // list stride in shared memory (entries; 33 words: lanes fall in distinct banks)
-constexpr int kTPart = 32;           // particles per cell the tile path handles (cell width ~2 lattice planes: 8 .. 27)
+constexpr int kTPass = 16;           // particles of a cell per pass (Q = 32 / P >= 2 streams each); 8 when lists overflow
+constexpr int kTPart = 64;           // particles per cell the tile path handles (cell width ~2 lattice planes: 8 .. 27)
 constexpr int kTQMax = 8;            // candidate streams per particle at most
+constexpr int kTRow = 32;            // hits one lane (one stream of one particle) can hold
+typedef uint16_t entry_t;            // a hit is the 16-bit shared address of the staged candidate
+constexpr int kTRowS = 34;           // list stride in shared memory (entries; 17 words: lanes fall in distinct banks)
+constexpr int kTBlocks = 5;          // resident blocks per SM (34 KB of shared memory, 48 registers)
 
 constexpr uint32_t kFull = 0xffffffffu;
 
@@ -58,9 +62,9 @@ struct Head {
 };
 
 constexpr size_t kBytesS32 = sizeof(float4) * kTCap;
-constexpr size_t kBytesB = sizeof(uint16_t) * kTWarps * 32 * kTRowS;
+constexpr size_t kBytesB = sizeof(entry_t) * kTWarps * 32 * kTRowS;
 constexpr size_t kSmemList = kBytesS32 + kBytesB + sizeof(Head);
-static_assert(4 * (kSmemList + 1024) <= 227 * 1024, "four blocks per SM");
+static_assert(kTBlocks * (kSmemList + 1024) <= 227 * 1024, "blocks per SM");
 static_assert(kBytesS32 + 1024 < 65536, "hits are kept as 16-bit shared addresses of the staged candidate");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -79,7 +83,7 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
     if (t < 64) {
         int cc[3];
         cell_coords(g, c0, cc[0], cc[1], cc[2]);
-        if (t < 3) H->gc[t] = cc[t];
+        if (t == 0) { H->gc[0] = cc[0]; H->gc[1] = cc[1]; H->gc[2] = cc[2]; }
         if (t < 12) H->shift[t] = (float)((double)((t & 3) - 1) * g.w[t >> 2]);
         const int o[3] = {(t & 3) - 1, ((t >> 2) & 3) - 1, (t >> 4) - 1};
         bool ok = true;
@@ -135,32 +139,42 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
     return total;
 }
 
-// One warp = one home cell of the group.  lane = q * P + p: particle p (of P), candidate stream q (of Q).
-struct Home {
-    int P, Q, lgq, p, q;
-    bool active;             // q < Q
+// One warp = one home cell of the group, worked on kTPass particles at a time.
+struct HomeCell {
+    int P;                   // particles in the cell
     uint32_t cs;             // first sorted particle of the cell
-    uint32_t selfc;          // window index of particle p
+    uint32_t c0;             // window index of its first particle
     int hx, hy, hz;
 };
 
-__device__ __forceinline__ Home home_of(const sph_grid &g, const Head *H, int w, int lane)
+__device__ __forceinline__ HomeCell home_cell(const sph_grid &g, const Head *H, int w)
 {
-    Home h;
+    HomeCell h;
     h.hx = w & 1; h.hy = (w >> 1) & 1; h.hz = w >> 2;
     const int wc = ((1 + h.hz) * 4 + (1 + h.hy)) * 4 + (1 + h.hx);
     // the last group of an odd layer count is half empty: its window cell is the periodic image of layer 0
     const bool exists = H->gc[0] + h.hx < g.ncl[0] && H->gc[1] + h.hy < g.ncl[1] && H->gc[2] + h.hz < g.ncl[2];
     h.P = exists ? (int)H->cnt[wc] : 0;
     h.cs = H->start[wc];
-    const int P = h.P > 0 ? h.P : 1;
-    h.Q = P <= 4 ? kTQMax : 32 / P;
-    h.lgq = 31 - __clz(h.Q);
-    h.q = (int)(((float)lane + 0.5f) * __frcp_rn((float)P));     // lane / P: never within 1/64 of an integer
-    h.p = lane - h.q * P;
-    h.active = h.q < h.Q;
-    h.selfc = H->off[wc] + (uint32_t)h.p;
+    h.c0 = H->off[wc];
     return h;
+}
+
+// lane = q * P + p: particle p (of the P <= 16 of this pass), candidate stream q (of Q = 32 / P)
+struct LaneMap {
+    int Q, lgq, p, q;
+    bool active;             // q < Q
+};
+
+__device__ __forceinline__ LaneMap lane_map(int P, int lane)
+{
+    LaneMap m;
+    m.Q = P <= 4 ? kTQMax : 32 / P;
+    m.lgq = 31 - __clz(m.Q);
+    m.q = (int)(((float)lane + 0.5f) * __frcp_rn((float)P));     // lane / P: never within 1/64 of an integer
+    m.p = lane - m.q * P;
+    m.active = m.q < m.Q;
+    return m;
 }
 
 // One candidate stream of one window column against one home particle, two candidates per trip.
@@ -178,11 +192,14 @@ __device__ __forceinline__ void test_one(uint32_t ptr, uint32_t selfptr, const f
             over = true;
         } else {
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(lp), "h"((unsigned short)ptr) : "memory");
-            lp += 2u;
+            lp += (uint32_t)sizeof(entry_t);
             maxacc = fmaxf(maxacc, rsq);
         }
     }
 }
+
+#define SPH_LDS4(X, Y, Z, W, ADDR) \
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(X), "=f"(Y), "=f"(Z), "=f"(W) : "r"(ADDR))
 
 template <bool CHECK, bool SELF>
 __device__ __forceinline__ void test_column(uint32_t ptr, uint32_t pend, uint32_t step, uint32_t selfptr,
@@ -190,25 +207,24 @@ __device__ __forceinline__ void test_column(uint32_t ptr, uint32_t pend, uint32_
                                             float &maxacc, bool &over)
 {
     float ax, ay, az, aw, bx, by, bz, bw;
-    for (; ptr + step < pend; ptr += 2u * step) {
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ax), "=f"(ay), "=f"(az), "=f"(aw) : "r"(ptr));
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(bx), "=f"(by), "=f"(bz), "=f"(bw) : "r"(ptr + step));
+    for (; ptr + step < pend; ptr += 2u * step) {                        // two loads in flight
+        SPH_LDS4(ax, ay, az, aw, ptr);
+        SPH_LDS4(bx, by, bz, bw, ptr + step);
         test_one<CHECK, SELF>(ptr, selfptr, hp, thr_out, ax, ay, az, lp, lp_lim, maxacc, over);
         test_one<CHECK, SELF>(ptr + step, selfptr, hp, thr_out, bx, by, bz, lp, lp_lim, maxacc, over);
     }
     if (ptr < pend) {
-        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(ax), "=f"(ay), "=f"(az), "=f"(aw) : "r"(ptr));
+        SPH_LDS4(ax, ay, az, aw, ptr);
         test_one<CHECK, SELF>(ptr, selfptr, hp, thr_out, ax, ay, az, lp, lp_lim, maxacc, over);
     }
 }
 
 // ------------------------------------------------------------------ neighbour kernel
-__global__ void __launch_bounds__(kTThreads, 4)
+__global__ void __launch_bounds__(kTThreads, kTBlocks)
 tile_list_kernel(const __grid_constant__ sph_grid g, const __grid_constant__ TileArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float4 *S32 = reinterpret_cast<float4 *>(smem);
-    uint16_t *Ball = reinterpret_cast<uint16_t *>(smem + kBytesS32);
     Head *H = reinterpret_cast<Head *>(smem + kBytesS32 + kBytesB);
 
     // positions far outside the box: single-shift semantics matter, the general path decides
@@ -226,82 +242,90 @@ tile_list_kernel(const __grid_constant__ sph_grid g, const __grid_constant__ Til
     }
 
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const Home hm = home_of(g, H, w, lane);
-    const int P = hm.P;
-    if (P == 0) return;
-    if (P > kTPart) {
+    const HomeCell hc = home_cell(g, H, w);
+    if (hc.P == 0) return;
+    if (hc.P > kTPart) {
         if (lane == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
         return;
     }
-    const uint32_t asorted = hm.cs + (uint32_t)hm.p;
-    uint16_t *B = Ball + (w * 32 + lane) * kTRowS;                       // this lane's list of hits
+    entry_t *B = reinterpret_cast<entry_t *>(smem + kBytesS32) + (w * 32 + lane) * kTRowS;     // this lane's list of hits
+    const uint32_t s32a = smem_u32(S32), s16 = s32a & 0xffffu;
+    const uint32_t lp0 = smem_u32(B), lp_lim = lp0 + (uint32_t)sizeof(entry_t) * kTRow;
+    const uint32_t *offh = H->off + (hc.hz * 4 + hc.hy) * 4 + hc.hx;
+    uint32_t wmax = 0;
 
-    const uint32_t s32a = smem_u32(S32);
-    const uint32_t selfptr = s32a + hm.selfc * 16u;
-    const float4 hp = S32[hm.selfc];
-    const uint32_t lp0 = smem_u32(B), lp_lim = lp0 + 2u * kTRow;
-    uint32_t lp = lp0;
-    float maxacc = 0.f;
-    bool over = false;
-    if (hm.active) {
-        const uint32_t step = (uint32_t)hm.Q * 16u;
-        const uint32_t *offh = H->off + (hm.hz * 4 + hm.hy) * 4 + hm.hx;
+    // Long rows (the default Verlet tolerance gives ~47 neighbours) overflow a stream's list at Q = 2:
+    // the cell is then redone with 8 particles per pass (Q >= 4) before the general kernel is asked.
+    int pass = kTPass;
+#pragma unroll 1
+    for (int p0 = 0; p0 < hc.P; p0 += pass) {
+        const int P = min(pass, hc.P - p0);
+        const LaneMap lm = lane_map(P, lane);
+        const uint32_t selfc = hc.c0 + (uint32_t)(p0 + lm.p), asorted = hc.cs + (uint32_t)(p0 + lm.p);
+        const uint32_t selfptr = s32a + selfc * 16u;
+        const float4 hp = S32[selfc];
+        uint32_t lp = lp0;
+        float maxacc = 0.f;
+        bool over = false;
+        if (lm.active) {
+            const uint32_t step = (uint32_t)lm.Q * 16u;
 #pragma unroll
-        for (int col = 0; col < 9; ++col) {
-            const uint32_t s = offh[((col / 3) * 4 + col % 3) * 4], e = offh[((col / 3) * 4 + col % 3) * 4 + 3];
-            const uint32_t pend = s32a + e * 16u, pbeg = s32a + (s + (uint32_t)hm.q) * 16u;
-            // this lane tests at most ((e - s) >> lgq) + 1 candidates of the column: with room for that
-            // many hits the loop needs no capacity test
-            const bool room = lp + 2u * (((e - s) >> hm.lgq) + 1u) <= lp_lim;
-            if (col == 4) {                                              // resolved by the unrolling
-                if (room) test_column<false, true>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
-                else test_column<true, true>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
-            } else {
-                if (room) test_column<false, false>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
-                else test_column<true, false>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
+            for (int col = 0; col < 9; ++col) {                          // unrolled: 4.43 ms against 4.55 ms as a loop
+                const uint32_t s = offh[((col / 3) * 4 + col % 3) * 4], e = offh[((col / 3) * 4 + col % 3) * 4 + 3];
+                const uint32_t pend = s32a + e * 16u, pbeg = s32a + (s + (uint32_t)lm.q) * 16u;
+                // this lane tests at most ((e - s) >> lgq) + 1 candidates of the column: with room for that
+                // many hits the loop needs no capacity test
+                const bool room = lp + (uint32_t)sizeof(entry_t) * (((e - s) >> lm.lgq) + 1u) <= lp_lim;
+                if (col == 4) {                                          // the column that holds the particle itself
+                    if (room) test_column<false, true>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
+                    else test_column<true, true>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
+                } else {
+                    if (room) test_column<false, false>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
+                    else test_column<true, false>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
+                }
             }
         }
-    }
-    if (__any_sync(kFull, over)) {
-        if (lane == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
-        return;
-    }
-    const uint32_t s16 = s32a & 0xffffu;
-    // rare: some hit of this lane lies in the fp32 error band -> the reference's fp64 predicate on all of them
-    if (maxacc >= a.thr_in) {
-        const int nl = (int)((lp - lp0) >> 1);
-        int m = 0;
-        for (int k = 0; k < nl; ++k) {
-            const uint16_t raw = B[k];
-            const int j = __float_as_int(S32[(((uint32_t)raw - s16) & 0xffffu) >> 4].w);
-            if (pair_exact(g, a.pos4, (int)asorted, j)) B[m++] = raw;
+        if (__any_sync(kFull, over)) {
+            if (pass > 8) {
+                pass = 8;
+                p0 = -pass;                                              // start the cell again
+                continue;
+            }
+            if (lane == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
+            return;
         }
-        lp = lp0 + 2u * (uint32_t)m;
-    }
-    const int cntl = (int)((lp - lp0) >> 1);
-    // concatenate the Q lists of a particle: offsets by a fixed-order walk over the streams
-    int offq = 0, tot = 0;
-#pragma unroll
-    for (int k = 0; k < kTQMax; ++k) {
-        const int v = __shfl_sync(kFull, cntl, (k * P + hm.p) & 31);
-        if (k < hm.Q) {
-            if (k < hm.q) offq += v;
+        // rare: some hit of this lane lies in the fp32 error band -> the reference's fp64 predicate on all of them
+        if (maxacc >= a.thr_in) {
+            const int nl = (int)((lp - lp0) / sizeof(entry_t));
+            int m = 0;
+            for (int k = 0; k < nl; ++k) {
+                const entry_t raw = B[k];
+                const int j = __float_as_int(S32[(((uint32_t)raw - s16) & 0xffffu) >> 4].w);
+                if (pair_exact(g, a.pos4, (int)asorted, j)) B[m++] = raw;
+            }
+            lp = lp0 + (uint32_t)sizeof(entry_t) * (uint32_t)m;
+        }
+        const int cntl = (int)((lp - lp0) / sizeof(entry_t));
+        // concatenate the Q lists of a particle: offsets by a fixed-order walk over the streams
+        int offq = 0, tot = 0;
+#pragma unroll 1
+        for (int k = 0; k < lm.Q; ++k) {                                 // Q is uniform across the warp
+            const int v = __shfl_sync(kFull, cntl, (k * P + lm.p) & 31);
+            offq += k < lm.q ? v : 0;
             tot += v;
         }
-    }
-    if (hm.active) {
-        int32_t *erow = a.nbr + ((size_t)(asorted >> 5) * (size_t)a.K + (size_t)offq) * 32 + (asorted & 31);
-        const int nw = min(cntl, a.K - offq);                            // entries beyond the capacity are dropped
-        for (int k = 0; k < nw; ++k) {
-            const uint32_t c16 = ((uint32_t)B[k] - s16) & 0xfff0u;       // 16 * window index
-            erow[(size_t)k * 32] = __float_as_int(*reinterpret_cast<const float *>(
-                reinterpret_cast<const unsigned char *>(S32) + c16 + 12));
+        if (lm.active) {
+            int32_t *erow = a.nbr + ((size_t)(asorted >> 5) * (size_t)a.K + (size_t)offq) * 32 + (asorted & 31);
+            const int nw = min(cntl, a.K - offq);                        // entries beyond the capacity are dropped
+            const unsigned char *Sw = reinterpret_cast<const unsigned char *>(S32) + 12;   // sorted index of a candidate
+            for (int k = 0; k < nw; ++k)
+                erow[k * 32] = *reinterpret_cast<const int *>(Sw + (((uint32_t)B[k] - s16) & 0xfff0u));
+            if (lm.q == 0) a.cnt[asorted] = tot;
+            wmax = max(wmax, (uint32_t)tot);
         }
-        if (hm.q == 0) a.cnt[asorted] = tot;
-    } else {
-        tot = 0;
+        __syncwarp();                                                    // lists are reused by the next pass
     }
-    const uint32_t wmax = __reduce_max_sync(kFull, (uint32_t)tot);
+    wmax = __reduce_max_sync(kFull, wmax);
     if (lane == 0) {
         if (wmax > *(volatile uint32_t *)&a.status->max_count) atomicMax(&a.status->max_count, wmax);
         if (wmax > (uint32_t)a.K) atomicOr(&a.status->flags, SPH_F_NBR_OVERFLOW);
