@@ -190,6 +190,27 @@ int sph_conduction(const sph_grid *grid, const sph_buffers *buf, const double *d
                    const double *d_h_orig, int h_uniform, int list_fresh, double *d_aux4, double *d_udot,
                    void *stream);
 
+/* Velocity gradient and Newtonian viscous pair force: the eta / zeta terms of
+ * spam_complete_force.SpamComplete (spam_complete_force.py:36-60,140-165).  BUILDER-DEFINED arithmetic:
+ * the reference computes them in the Fortran routine sphforce3d, which it does not ship (SURVEY.md
+ * section 8c), so these two follow the in-repo conventions instead --
+ *   gradv_i[a][b] = sum_j (m_j / rho_j) (v_j - v_i)_a dW_ij/dx_b      (properties.py:95-98 with the
+ *                   weight of c_properties.pyx:166-188 and the FINAL density, so the result does not
+ *                   depend on the pair order as the reference's running-density loop does)
+ *                   dW_ij is the gradient with respect to r_j - r_i as everywhere in the reference, so
+ *                   gradv estimates MINUS the velocity gradient (v = A r gives gradv ~ -A)
+ *   pi = 2 eta symmetric_traceless(gradv) + zeta tr(gradv) I             (tensor.py:5-16; this is
+ *                   -2 eta S - zeta (div v) I for the true gradient: shear heats the fluid)
+ *   a  = (pi_i / rho_i^2 + pi_j / rho_j^2) . dW_ij, +a to i, -a to j;  du = a . dv / 2,
+ *   udot_i += du m_j, udot_j += du m_i                                  (forces.py:353-368, tensor for scalar)
+ * d_gradv is [n,3,3] in original order; d_aux4 / d_aux8 are caller-owned scratch of n*4 / n*8 doubles
+ * (32-byte aligned).  sph_viscous_force ACCUMULATES into vdot / udot like sph_force. */
+int sph_gradv(const sph_grid *grid, const sph_buffers *buf, const double *d_rho, const double *d_h_orig,
+              int h_uniform, int list_fresh, double *d_aux4, double *d_gradv, void *stream);
+int sph_viscous_force(const sph_grid *grid, const sph_buffers *buf, const double *d_gradv, const double *d_rho,
+                      double eta, double zeta, const double *d_h_orig, int h_uniform, int list_fresh,
+                      double fcutoff, double *d_aux8, double *d_vdot, double *d_udot, void *stream);
+
 /* ------------------------------------------------------------------ pair-list API surface */
 
 /* Lexicographic i<j pair list in ORIGINAL indices (what VerletList.build leaves in

@@ -103,6 +103,9 @@ SIGNATURES = {
                                  _vp, _vp, _vp]),
     "sph_pressure_term": (ctypes.c_int, [_bp, _vp, _vp, _i32, _vp]),
     "sph_conduction": (ctypes.c_int, [_gp, _bp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
+    "sph_gradv": (ctypes.c_int, [_gp, _bp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
+    "sph_viscous_force": (ctypes.c_int, [_gp, _bp, _vp, _vp, _dbl, _dbl, _vp, ctypes.c_int, ctypes.c_int, _dbl,
+                                         _vp, _vp, _vp, _vp]),
     "sph_pairs_count": (ctypes.c_int, [_bp, _vp, _vp]),
     "sph_pairs_fill": (ctypes.c_int, [_bp, _vp, _vp, _i64, _vp]),
     "sph_exclusive_scan_u32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp]),

@@ -187,6 +187,22 @@ class NeighbourBackend(object):
                                       int(self.fresh), _ptr(aux4), _ptr(_f64(udot, "udot")), _stream()),
               "sph_conduction")
 
+    def gradv(self, rho, h, h_uniform, gradv):
+        """sph_gradv: velocity gradient tensor [n,3,3] with the final density (builder-defined, see the header)."""
+        aux4 = self._alloc("aux4", 4 * self.n, torch.float64)
+        check(self.lib.sph_gradv(ctypes.byref(self.grid), ctypes.byref(self.buf), _ptr(_f64(rho, "rho")),
+                                 _ptr(_f64(h, "h")), int(bool(h_uniform)), int(self.fresh), _ptr(aux4),
+                                 _ptr(_f64(gradv, "gradv")), _stream()), "sph_gradv")
+
+    def viscous_force(self, gradv, rho, eta, zeta, h, h_uniform, fcutoff, vdot, udot):
+        """sph_viscous_force: Newtonian stress pair force, accumulated into vdot / udot."""
+        aux8 = self._alloc("aux8", 8 * self.n, torch.float64)
+        check(self.lib.sph_viscous_force(ctypes.byref(self.grid), ctypes.byref(self.buf), _ptr(_f64(gradv, "gradv")),
+                                         _ptr(_f64(rho, "rho")), float(eta), float(zeta), _ptr(_f64(h, "h")),
+                                         int(bool(h_uniform)), int(self.fresh), float(fcutoff), _ptr(aux8),
+                                         _ptr(_f64(vdot, "vdot")), _ptr(_f64(udot, "udot")), _stream()),
+              "sph_viscous_force")
+
     def compress(self):
         check(self.lib.sph_compress(ctypes.byref(self.grid), ctypes.byref(self.buf), _stream()), "sph_compress")
 

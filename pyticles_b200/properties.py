@@ -7,7 +7,8 @@ neighbour structure (sph_density_eos): rho, p, pco, u, t are overwritten in plac
 reference does.  Reference quirks that are kept because they are the semantics
 (SURVEY.md fact 8): the self term is W(0; h[0]) for every particle, the kernel normalisation
 is always 3-D, a pair uses h of its first member.  `gradv` is order dependent in the
-reference (running rho, properties.py:95-98) and is not computed.
+reference (running rho, properties.py:95-98): spam_properties leaves it alone, and `spam_gradv`
+computes the order-independent two-pass version (builder-defined, see sph_gradv in the header).
 """
 import torch
 
@@ -83,6 +84,15 @@ def spam_properties(p, nl, hs=None, hl=None, eos=None, long_range=False):
         p.t[n:] = vdw_temp(p.rho[n:], p.u[n:])
     for name in ("wij", "dwij", "wij_lr", "dwij_lr"):
         nl._pairs.pop(name, None)
+
+
+def spam_gradv(p, nl):
+    """p.gradv[i, a, b] = sum_j (m_j / rho_j) (v_j - v_i)_a dW_ij/dx_b with the FINAL density p.rho
+    (call after spam_properties).  Builder-defined: properties.py:95-98 uses the running density, so
+    its result depends on the pair order; the weight is the one of c_properties.pyx:166-188.  As in the
+    reference dW_ij is the gradient with respect to r_j - r_i, so this is MINUS the velocity gradient."""
+    nl._refresh_sorted()
+    nl.backend.gradv(p.rho, p.h, _h_uniform(p, p.h), p.gradv)
 
 
 def spam_properties_ls(p, nl):
