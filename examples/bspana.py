@@ -5,8 +5,11 @@ SpamForce instead of the Fortran-only SpamComplete viscous terms).
 
     python examples/bspana.py [steps] [side]
 """
+import os
 import sys
 from time import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))      # run from a checkout
 
 import numpy as np
 

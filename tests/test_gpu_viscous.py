@@ -153,3 +153,26 @@ def test_spam_complete_with_viscosity():
     assert rel_err(P, want) < RTOL
     with pytest.raises(NotImplementedError):
         spam_complete_force.SpamComplete(p, nl).apply()               # default cgrad = 1.0
+
+
+def test_nanobox_quench_example_runs(capsys):
+    """examples/nanobox_quench.py (the reference's showcase set-up, nanobox_quench.py:57-101) for a few
+    steps: finite state, positive densities, thermostat holds the temperature."""
+    import importlib.util
+    import os
+    import sys
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "nanobox_quench.py")
+    spec = importlib.util.spec_from_file_location("nanobox_quench_example", path)
+    argv = sys.argv
+    sys.argv = [path, "12", "8"]
+    try:
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        p, steps = mod.main()
+    finally:
+        sys.argv = argv
+    assert steps == 12
+    n = p.n
+    assert bool(torch.isfinite(p.r[:n]).all()) and bool(torch.isfinite(p.v[:n]).all())
+    assert float(p.rho[:n].min()) > 0.0
+    assert abs(float(p.t[:n].mean()) - 0.8) < 0.05
