@@ -16,7 +16,7 @@
 // Exactness is the one of the general kernel: rsq32 < thr_in accepts, rsq32 >= thr_out rejects,
 // hits inside the fp32 error band are decided by the reference's fp64 predicate (pair_exact).
 // Cases outside the fixed capacities (> 64 particles in a cell, > 32 hits in one stream's list even
-// at Q >= 4, > 1024 particles in the 64 cells of a window, positions far outside the box) raise
+// at Q >= 4, > 1536 particles in the 64 cells of a window, positions far outside the box) raise
 // SPH_F_TILE_FALLBACK and the general kernel redoes the pass.
 //
 // Reference semantics (file:line into the reference tree):
@@ -30,14 +30,14 @@ namespace {
 
 constexpr int kTWarps = 8;           // warps per block = cells per group
 constexpr int kTThreads = kTWarps * 32;
-constexpr int kTCap = 1024;          // staged candidates per group (64 cells)
+constexpr int kTCap = 1536;          // staged candidates per group (64 cells): the most that leaves 5 blocks per SM
 constexpr int kTPass = 16;           // particles of a cell per pass (Q = 32 / P >= 2 streams each); 8 when lists overflow
 constexpr int kTPart = 64;           // particles per cell the tile path handles (cell width ~2 lattice planes: 8 .. 27)
 constexpr int kTQMax = 8;            // candidate streams per particle at most
 constexpr int kTRow = 32;            // hits one lane (one stream of one particle) can hold
 typedef uint16_t entry_t;            // a hit is the 16-bit shared address of the staged candidate
 constexpr int kTRowS = 34;           // list stride in shared memory (entries; 17 words: lanes fall in distinct banks)
-constexpr int kTBlocks = 5;          // resident blocks per SM (34 KB of shared memory, 48 registers)
+constexpr int kTBlocks = 5;          // resident blocks per SM (43 KB of shared memory, 48 registers)
 
 constexpr uint32_t kFull = 0xffffffffu;
 
@@ -50,6 +50,7 @@ struct TileArgs {
     int32_t *cnt;
     sph_status *status;
     float thr_in, thr_out;
+    int pass0;               // particles of a cell per pass to start with (16 or 8)
 };
 
 // shared memory of a block: [S32 | B | Head]
@@ -238,8 +239,9 @@ __device__ __forceinline__ uint32_t tile_cell(const sph_grid &g, const TileArgs 
     uint32_t wmax = 0;
 
     // Long rows (the default Verlet tolerance gives ~47 neighbours) overflow a stream's list at Q = 2:
-    // the cell is then redone with 8 particles per pass (Q >= 4) before the general kernel is asked.
-    int pass = kTPass;
+    // the launcher then starts at 8 particles per pass (Q >= 4); a cell that overflows at 16 is redone
+    // at 8 before the general kernel is asked.
+    int pass = a.pass0;
 #pragma unroll 1
     for (int p0 = 0; p0 < hc.P; p0 += pass) {
         const int P = min(pass, hc.P - p0);
@@ -382,6 +384,10 @@ TileArgs base_args(const sph_grid *g, const sph_buffers *b)
     a.cnt = b->cnt;
     a.status = b->status;
     tile_thresholds(g, &a.thr_in, &a.thr_out);
+    // expected neighbours per particle at the mean density of the local grid: a stream of Q = 2 holds 32 hits
+    const double vol = (g->ncl[0] * g->w[0]) * (g->ncl[1] * g->w[1]) * (g->ncl[2] * g->w[2]);
+    const double expect = vol > 0.0 ? 4.18879 * g->thr * sqrt(g->thr) * (double)b->n / vol : 0.0;
+    a.pass0 = expect > 38.0 ? 8 : kTPass;
     return a;
 }
 

@@ -52,7 +52,8 @@ def main():
     from pyticles_b200.array import parray
     peak, _ = bench.peaks()
     dev = torch.device("cuda", 0)
-    print("# N, density, cutoff, pairs/particle, ms per build, particles/s, pairs/s, alg GB/s, frac of %.0f GB/s" % peak)
+    print("# N, density, cutoff, pairs/particle, ms per build, particles/s, pairs/s, alg GB/s, frac of %.0f GB/s, "
+          "neighbour kernel (tile = cell-group kernel, general = warp-per-cell kernel after SPH_F_TILE_FALLBACK)" % peak)
     for logn in (20, 22, 24, 26, 28):
         n_target = 1 << logn
         if n_target > a.max_n:
@@ -82,8 +83,9 @@ def main():
             ms = e0.elapsed_time(e1) / a.reps
             pairs = nl.nip
             gbs = (24.0 * n + 8.0 * pairs) / (ms * 1e-3) / 1e9
-            print("%10d %4.1f %4.1f %7.2f %9.3f %.3e %.3e %8.1f %.4f" %
-                  (n, rho, rc, pairs / n, ms, n / (ms * 1e-3), pairs / (ms * 1e-3), gbs, gbs / peak), flush=True)
+            which = "general" if nl.backend.status().flags & 32 else "tile"
+            print("%10d %4.1f %4.1f %7.2f %9.3f %.3e %.3e %8.1f %.4f %s" %
+                  (n, rho, rc, pairs / n, ms, n / (ms * 1e-3), pairs / (ms * 1e-3), gbs, gbs / peak, which), flush=True)
             del p, nl, r, v
             torch.cuda.empty_cache()
 
