@@ -173,3 +173,35 @@ def test_evaluator_against_oracle():
     for name in ("rho", "p", "pco", "u", "vdot", "udot"):
         assert rel_err(_np(getattr(p, name))[:n], ref[name]) < 1e-10, name
     assert np.array_equal(_np(nl.backend.export_pairs()).astype(np.int64), ref["iap"].astype(np.int64))
+
+
+def test_positions_slightly_outside_the_box_stay_on_the_tile_kernel():
+    """Particles up to 0.3 outside [0, L) (an integrator step before the box is applied): binned by their
+    periodic image, paired under the reference's single-shift minimum image -- no fallback needed."""
+    from pyticles_b200 import _lib
+    r, v, box = O.lattice_workload(16, 14, 12, seed=43, jitter=0.1)
+    rng = np.random.default_rng(13)
+    n = r.shape[0]
+    edge = np.any((r < 0.8) | (r > np.array(box) - 0.8), axis=1)
+    r[edge] += rng.uniform(-0.7, 0.7, size=(int(edge.sum()), 3))
+    assert (r < 0).any() and (r > np.array(box)).any()
+    m, h, t = np.ones(n), np.full(n, 2.0), np.ones(n)
+    ref = C.sph_step(r, v, m, h, t, np.array(box), 2.0, 0.0, 5.0)
+    p = make_system(r, v, m, h, t, box)
+    nl = run_step(p, 2.0, 0.0, 5.0)
+    flags = nl.backend.status().flags
+    assert flags & _lib.SPH_F_OUT_OF_BOX and not flags & (_lib.SPH_F_OUT_OF_RANGE | _lib.SPH_F_TILE_FALLBACK)
+    check_against(p, nl, ref, n)
+
+
+def test_default_verlet_tolerance_stays_on_the_tile_kernel():
+    """VerletList's default tolerance (1.0, neighbour_list.py:153): ~47 neighbours per particle, rows of
+    up to ~70 -- the launcher starts at 8 particles per pass and nothing falls back."""
+    r, v, box = O.lattice_workload(27, 27, 27, seed=45, jitter=0.3)
+    n = r.shape[0]
+    m, h, t = np.ones(n), np.full(n, 2.0), np.ones(n)
+    ref = C.sph_step(r, v, m, h, t, np.array(box), 2.0, 1.0, 5.0)
+    p = make_system(r, v, m, h, t, box)
+    nl = run_step(p, 2.0, 1.0, 5.0)
+    assert not fallback_flag(nl)
+    check_against(p, nl, ref, n, pair_arrays=False)
