@@ -128,3 +128,35 @@ def test_empty_and_single():
         r = np.zeros((n, 3))
         assert O.verlet_build(r, r, (5., 5., 5.), 2.0, 1.0)["iap"].shape == (0, 2)
         assert C.build_pairs(r, np.array([5., 5., 5.]), 2.0, 1.0).shape == (0, 2)
+
+
+def test_builder_defined_viscous_statement_invariants():
+    """oracle.gradv_two_pass / newtonian_stress / viscous_force are NOT restatements of the reference (its
+    viscous arithmetic lives in the absent Fortran sphforce3d): they state the formulas the CUDA path defines,
+    and the GPU suite compares the kernels with them.  Here: the invariants those formulas must have."""
+    L = 10
+    r, v, box = O.lattice_workload(L, L, L, seed=3, jitter=0.0)
+    n = r.shape[0]
+    m, h, t = np.ones(n), np.full(n, 2.0), np.ones(n)
+    iap = C.build_pairs(r, np.array(box), 2.0, 0.0).astype(np.int64)
+    A = np.array([[0.0, 0.02, -0.01], [-0.02, 0.0, 0.03], [0.01, -0.03, 0.0]])       # rigid rotation
+    vrot = r @ A.T
+    drij, rij, rsq, dv = O.separations(iap, r, vrot, box)
+    pr = O.spam_properties(n, m, h, t, iap, rij, drij)
+    g = O.gradv_two_pass(n, m, pr["rho"], iap, dv, pr["dwij"])
+    bulk = np.all((r > 3.0) & (r < np.array(box) - 3.0), axis=1)
+    c = g[bulk][0, 0, 1] / A[0, 1]
+    assert -1.1 < c < -0.9                                           # gradv ~ -grad v (dW taken w.r.t. r_j - r_i)
+    assert np.allclose(g[bulk], c * A, rtol=0, atol=1e-13)
+    assert np.abs(O.newtonian_stress(g[bulk], 1.0, 0.1)).max() < 1e-13          # no stress under rigid rotation
+    # uniform translation: no gradient at all
+    drij, rij, rsq, dv0 = O.separations(iap, r, np.tile([0.3, -0.2, 0.1], (n, 1)), box)
+    assert np.abs(O.gradv_two_pass(n, m, pr["rho"], iap, dv0, pr["dwij"])).max() == 0.0
+    # a shear wave is decelerated and heats the fluid; the pair force is antisymmetric
+    vs = np.stack([0.1 * np.sin(2 * np.pi * r[:, 1] / L), np.zeros(n), np.zeros(n)], axis=1)
+    drij, rij, rsq, dv = O.separations(iap, r, vs, box)
+    g = O.gradv_two_pass(n, m, pr["rho"], iap, dv, pr["dwij"])
+    vd, ud = O.viscous_force(n, m, O.newtonian_stress(g, 1.0, 0.0), pr["rho"], iap, rij, pr["dwij"], dv)
+    assert np.abs(vd.sum(axis=0)).max() < 1e-13 * np.abs(vd).sum()
+    assert ud.sum() > 0.0 and (vd[:, 0] * vs[:, 0]).sum() < 0.0
+    assert abs(ud.sum() + (vd * vs).sum()) < 1e-12 * abs(ud.sum())               # kinetic energy lost = heat gained
