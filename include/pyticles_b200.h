@@ -50,7 +50,7 @@ enum {
                                  sph_status.max_count says how many are needed */
     SPH_F_OUT_OF_SLAB = 16,   /* a particle lies outside the local cell-layer range */
     SPH_F_TILE_FALLBACK = 32  /* the cell-group (tile) neighbour kernel met a case outside its
-                                 fixed capacities (a cell with > 64 particles, > 1536 particles
+                                 fixed capacities (a cell with > 64 particles, > 1280 particles
                                  in the 64 cells around a group, > 32 hits in one stream's list,
                                  positions far outside the box): the general kernel did the
                                  pass.  The neighbour structure is the same either way (rows

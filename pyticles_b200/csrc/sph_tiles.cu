@@ -16,7 +16,7 @@
 // Exactness is the one of the general kernel: rsq32 < thr_in accepts, rsq32 >= thr_out rejects,
 // hits inside the fp32 error band are decided by the reference's fp64 predicate (pair_exact).
 // Cases outside the fixed capacities (> 64 particles in a cell, > 32 hits in one stream's list even
-// at Q >= 4, > 1536 particles in the 64 cells of a window, positions far outside the box) raise
+// at Q >= 4, > 1280 particles in the 64 cells of a window, positions far outside the box) raise
 // SPH_F_TILE_FALLBACK and the general kernel redoes the pass.
 //
 // Reference semantics (file:line into the reference tree):
@@ -30,14 +30,15 @@ namespace {
 
 constexpr int kTWarps = 8;           // warps per block = cells per group
 constexpr int kTThreads = kTWarps * 32;
-constexpr int kTCap = 1536;          // staged candidates per group (64 cells): the most that leaves 5 blocks per SM
+constexpr int kTCap = 1280;          // staged candidates per group (64 cells); 1536 still fits 5 blocks per SM but
+                                     // leaves 13 KB of L1: 4.46 against 4.35 ms on 256^3
 constexpr int kTPass = 16;           // particles of a cell per pass (Q = 32 / P >= 2 streams each); 8 when lists overflow
 constexpr int kTPart = 64;           // particles per cell the tile path handles (cell width ~2 lattice planes: 8 .. 27)
 constexpr int kTQMax = 8;            // candidate streams per particle at most
 constexpr int kTRow = 32;            // hits one lane (one stream of one particle) can hold
 typedef uint16_t entry_t;            // a hit is the 16-bit shared address of the staged candidate
 constexpr int kTRowS = 34;           // list stride in shared memory (entries; 17 words: lanes fall in distinct banks)
-constexpr int kTBlocks = 5;          // resident blocks per SM (43 KB of shared memory, 48 registers)
+constexpr int kTBlocks = 5;          // resident blocks per SM (38 KB of shared memory, 48 registers)
 
 constexpr uint32_t kFull = 0xffffffffu;
 

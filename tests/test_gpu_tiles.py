@@ -119,7 +119,7 @@ def test_capacity_limits_fall_back_to_the_general_kernel(kind):
     r, v, box = O.lattice_workload(12, 12, 12, seed=35, jitter=0.1)
     if kind == "crowded_cell":          # 70 more particles in one cell (> 64 per cell)
         extra = np.array([5.0, 5.0, 5.0]) + rng.uniform(0.0, 0.5, size=(70, 3))
-    elif kind == "crowded_window":      # 4.5 particles per unit volume: > 1536 candidates around a group
+    elif kind == "crowded_window":      # 4.5 particles per unit volume: > 1280 candidates around a group
         extra = rng.uniform(0.0, 12.0, size=(6000, 3))
     else:                               # a tight cluster of 45: streams of its cell (and of the cells around) list > 32 hits even at Q = 4
         extra = np.array([3.05, 3.05, 3.05]) + rng.uniform(0.0, 0.9, size=(45, 3))
