@@ -205,3 +205,63 @@ def test_default_verlet_tolerance_stays_on_the_tile_kernel():
     nl = run_step(p, 2.0, 1.0, 5.0)
     assert not fallback_flag(nl)
     check_against(p, nl, ref, n, pair_arrays=False)
+
+
+def _pairs(r, box, cutoff, tol, on, slab=None):
+    from pyticles_b200 import neighbour_list
+    n = r.shape[0]
+    with tiles(on):
+        p = make_system(r, np.zeros_like(r), np.ones(n), np.full(n, 2.0), np.ones(n), box)
+        nl = neighbour_list.VerletList(p, cutoff=cutoff, tolerance=tol)
+        nl.build()
+        return _np(nl.iap).astype(np.int64), fallback_flag(nl)
+
+
+@pytest.mark.parametrize("jitter", [0.0, 1e-9, 1e-7])
+def test_pairs_at_the_cutoff_are_decided_by_the_fp64_predicate(jitter):
+    """Unit lattice, cutoff 2: six neighbours of every particle sit at distance 2 (+- jitter), inside the fp32
+    error band.  `rsq < cutoff^2` is strict (neighbour_list.py:178): at jitter 0 they are all out."""
+    r, v, box = O.lattice_workload(12, 12, 12, seed=61, jitter=0.0)
+    if jitter:
+        r = r + np.random.default_rng(5).uniform(-jitter, jitter, size=r.shape)
+    ref = C.build_pairs(r, np.array(box), 2.0, 0.0).astype(np.int64)
+    if jitter == 0.0:
+        assert ref.shape[0] == r.shape[0] * 13            # 26 neighbours within r < 2, none at r == 2
+    got, fb = _pairs(r, box, 2.0, 0.0, True)
+    assert not fb
+    assert np.array_equal(got, ref)
+
+
+def test_random_geometries_tile_and_general_kernels_agree():
+    """Forty random boxes -- anisotropic, odd layer counts, lattices, gases and clustered gases, several
+    cutoffs and tolerances: the two neighbour kernels must produce the same lexicographic pair list, and
+    the first of each kind is also checked against the C oracle."""
+    rng = np.random.default_rng(2026)
+    kinds_checked = set()
+    n_tile = 0
+    for case in range(40):
+        kind = ("lattice", "gas", "clustered")[case % 3]
+        cutoff = float(rng.choice([1.5, 2.0, 2.0, 2.5]))
+        tol = float(rng.choice([0.0, 0.0, 0.5, 1.0]))
+        dims = rng.integers(7, 19, size=3)
+        if kind == "lattice":
+            r, v, box = O.lattice_workload(int(dims[0]), int(dims[1]), int(dims[2]), seed=100 + case,
+                                           jitter=float(rng.choice([0.0, 0.1, 0.3, 0.45])))
+        else:
+            box = tuple(float(d) for d in dims)
+            n = int(np.prod(dims) * rng.uniform(0.3, 1.5))
+            r = rng.random((n, 3)) * np.array(box)
+            if kind == "clustered":                        # a third of the particles in a few tight blobs
+                k = n // 3
+                centres = rng.random((5, 3)) * np.array(box)
+                r[:k] = centres[rng.integers(0, 5, k)] + rng.normal(scale=0.6, size=(k, 3))
+                r = np.mod(r, np.array(box))
+        a, fb_a = _pairs(r, box, cutoff, tol, True)
+        b, fb_b = _pairs(r, box, cutoff, tol, False)
+        assert not fb_b
+        assert np.array_equal(a, b), (case, kind, cutoff, tol, dims)
+        n_tile += not fb_a
+        if kind not in kinds_checked:
+            kinds_checked.add(kind)
+            assert np.array_equal(a, C.build_pairs(r, np.array(box), cutoff, tol).astype(np.int64)), (case, kind)
+    assert n_tile >= 25            # the tile kernel is the one that ran in most cases
