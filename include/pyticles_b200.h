@@ -254,6 +254,18 @@ int sph_slab_select(const double *d_x, int64_t stride, int32_t n, double inv_w, 
                     int32_t layer_left, int32_t layer_right, int32_t *d_idx_left, int32_t *d_idx_right,
                     int32_t cap, uint32_t *d_counts, void *stream);
 
+/* Halo rows of the slab decomposition: 10 doubles per boundary particle (r[3], v[3], m, h, t, global id as a
+ * double).  pack gathers the particles d_idx[0..n_idx) into d_rows; unpack scatters received rows to the
+ * particle slots first .. first + n_rows (the ghosts sit behind the owned particles).  pack2 / unpack2 do the
+ * same for two per-particle scalars (p and rho, the second exchange of an evaluation). */
+int sph_halo_pack(const int64_t *d_idx, int64_t n_idx, const double *d_r, const double *d_v, const double *d_m,
+                  const double *d_h, const double *d_t, const int64_t *d_gid, double *d_rows, void *stream);
+int sph_halo_unpack(const double *d_rows, int64_t n_rows, int64_t first, double *d_r, double *d_v, double *d_m,
+                    double *d_h, double *d_t, int64_t *d_gid, void *stream);
+int sph_halo_pack2(const int64_t *d_idx, int64_t n_idx, const double *d_a, const double *d_b, double *d_out,
+                   void *stream);
+int sph_halo_unpack2(const double *d_in, int64_t n_rows, int64_t first, double *d_a, double *d_b, void *stream);
+
 /* ------------------------------------------------------------------ stepping helpers ("next" rows) */
 
 /* x <- a + s * b over len doubles: the state-vector updates of integrator.py:37-41,44-59,62-95. */

@@ -114,6 +114,10 @@ SIGNATURES = {
     "sph_compress": (ctypes.c_int, [_gp, _bp, _vp]),
     "sph_ponder_rebuild": (ctypes.c_int, [_vp, _vp, _i32, _dbl, _vp, _vp]),
     "sph_slab_select": (ctypes.c_int, [_vp, _i64, _i32, _dbl, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "sph_halo_pack": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sph_halo_unpack": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sph_halo_pack2": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "sph_halo_unpack2": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "sph_axpy": (ctypes.c_int, [_vp, _vp, _vp, _dbl, _i64, _vp]),
     "sph_box_apply": (ctypes.c_int, [_d3, ctypes.c_int, _vp, _vp, _i32, _vp]),
 }

@@ -974,6 +974,59 @@ slab_select_kernel(const double *__restrict__ x, int64_t stride, int n, double i
     if (r && br + __popc(mr & lt) < cap) idx_right[br + __popc(mr & lt)] = i;
 }
 
+// Halo exchange of the slab decomposition: one row of 10 doubles per boundary particle
+// (r, v, m, h, t, global id), packed / unpacked in one pass each instead of a dozen tensor operations.
+__global__ void __launch_bounds__(kBlock)
+halo_pack_kernel(const int64_t *__restrict__ idx, int64_t n, const double *__restrict__ r,
+                 const double *__restrict__ v, const double *__restrict__ m, const double *__restrict__ h,
+                 const double *__restrict__ t, const int64_t *__restrict__ gid, double *__restrict__ rows)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t i = (size_t)idx[k];
+    double *o = rows + 10 * (size_t)k;
+    o[0] = r[3 * i]; o[1] = r[3 * i + 1]; o[2] = r[3 * i + 2];
+    o[3] = v[3 * i]; o[4] = v[3 * i + 1]; o[5] = v[3 * i + 2];
+    o[6] = m[i]; o[7] = h[i]; o[8] = t[i];
+    o[9] = (double)gid[i];
+}
+
+__global__ void __launch_bounds__(kBlock)
+halo_unpack_kernel(const double *__restrict__ rows, int64_t n, int64_t first, double *__restrict__ r,
+                   double *__restrict__ v, double *__restrict__ m, double *__restrict__ h,
+                   double *__restrict__ t, int64_t *__restrict__ gid)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t i = (size_t)(first + k);
+    const double *o = rows + 10 * (size_t)k;
+    r[3 * i] = o[0]; r[3 * i + 1] = o[1]; r[3 * i + 2] = o[2];
+    v[3 * i] = o[3]; v[3 * i + 1] = o[4]; v[3 * i + 2] = o[5];
+    m[i] = o[6]; h[i] = o[7]; t[i] = o[8];
+    gid[i] = (int64_t)o[9];
+}
+
+__global__ void __launch_bounds__(kBlock)
+halo_pack2_kernel(const int64_t *__restrict__ idx, int64_t n, const double *__restrict__ a,
+                  const double *__restrict__ b, double *__restrict__ out)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t i = (size_t)idx[k];
+    out[2 * k] = a[i];
+    out[2 * k + 1] = b[i];
+}
+
+__global__ void __launch_bounds__(kBlock)
+halo_unpack2_kernel(const double *__restrict__ in, int64_t n, int64_t first, double *__restrict__ a,
+                    double *__restrict__ b)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    a[first + k] = in[2 * k];
+    b[first + k] = in[2 * k + 1];
+}
+
 inline int blocks_for(int64_t n, int per) { return (int)((n + per - 1) / per); }
 
 inline int launch_status()
@@ -1391,6 +1444,42 @@ int sph_slab_select(const double *d_x, int64_t stride, int32_t n, double inv_w, 
     if (n > 0)
         slab_select_kernel<<<blocks_for(n, kBlock), kBlock, 0, s>>>(d_x, stride, n, inv_w, nc, layer_left,
                                                                     layer_right, d_idx_left, d_idx_right, (uint32_t)cap, d_counts);
+    return launch_status();
+}
+
+int sph_halo_pack(const int64_t *d_idx, int64_t n_idx, const double *d_r, const double *d_v, const double *d_m,
+                  const double *d_h, const double *d_t, const int64_t *d_gid, double *d_rows, void *stream)
+{
+    if (n_idx < 0 || (n_idx > 0 && (!d_idx || !d_r || !d_v || !d_m || !d_h || !d_t || !d_gid || !d_rows))) return SPH_E_BADARG;
+    if (n_idx > 0)
+        halo_pack_kernel<<<blocks_for(n_idx, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_idx, n_idx, d_r, d_v, d_m, d_h,
+                                                                                        d_t, d_gid, d_rows);
+    return launch_status();
+}
+
+int sph_halo_unpack(const double *d_rows, int64_t n_rows, int64_t first, double *d_r, double *d_v, double *d_m,
+                    double *d_h, double *d_t, int64_t *d_gid, void *stream)
+{
+    if (n_rows < 0 || first < 0 || (n_rows > 0 && (!d_rows || !d_r || !d_v || !d_m || !d_h || !d_t || !d_gid))) return SPH_E_BADARG;
+    if (n_rows > 0)
+        halo_unpack_kernel<<<blocks_for(n_rows, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_rows, n_rows, first, d_r, d_v,
+                                                                                           d_m, d_h, d_t, d_gid);
+    return launch_status();
+}
+
+int sph_halo_pack2(const int64_t *d_idx, int64_t n_idx, const double *d_a, const double *d_b, double *d_out, void *stream)
+{
+    if (n_idx < 0 || (n_idx > 0 && (!d_idx || !d_a || !d_b || !d_out))) return SPH_E_BADARG;
+    if (n_idx > 0)
+        halo_pack2_kernel<<<blocks_for(n_idx, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_idx, n_idx, d_a, d_b, d_out);
+    return launch_status();
+}
+
+int sph_halo_unpack2(const double *d_in, int64_t n_rows, int64_t first, double *d_a, double *d_b, void *stream)
+{
+    if (n_rows < 0 || first < 0 || (n_rows > 0 && (!d_in || !d_a || !d_b))) return SPH_E_BADARG;
+    if (n_rows > 0)
+        halo_unpack2_kernel<<<blocks_for(n_rows, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_in, n_rows, first, d_a, d_b);
     return launch_status();
 }
 

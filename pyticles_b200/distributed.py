@@ -65,18 +65,26 @@ class SlabDecomposition(object):
         return torch.searchsorted(b, layer, right=True)
 
     # ------------------------------------------------------------------ exchange primitive
-    def _exchange(self, rows, dest, splits=None):
-        """Send row k to rank dest[k]; returns (received rows, send order, send splits, recv splits)."""
+    def _exchange(self, rows, dest, splits=None, send_counts=None):
+        """Send row k to rank dest[k]; returns (received rows, (send order, send splits, recv splits)).
+        `send_counts` (host list, one count per rank) says the rows are already grouped by destination
+        rank in rank order: no sort, no histogram, one host round trip (the receive counts) instead of two."""
         W = self.world
-        if splits is None:
+        if splits is not None:
+            order, send_splits, recv_splits = splits
+        elif send_counts is not None:
+            order, send_splits = None, [int(c) for c in send_counts]
+            counts = torch.tensor(send_splits, dtype=torch.int64, device=rows.device)
+            rc = torch.empty_like(counts)
+            dist.all_to_all_single(rc, counts, group=self.group)
+            recv_splits = rc.tolist()
+        else:
             order = torch.argsort(dest, stable=True)
             counts = torch.bincount(dest, minlength=W)
             rc = torch.empty_like(counts)
             dist.all_to_all_single(rc, counts, group=self.group)
             send_splits, recv_splits = counts.tolist(), rc.tolist()
-        else:
-            order, send_splits, recv_splits = splits
-        send = rows[order].contiguous()
+        send = rows.contiguous() if order is None else rows[order].contiguous()
         recv = torch.empty((sum(recv_splits), rows.shape[1]), dtype=rows.dtype, device=rows.device)
         dist.all_to_all_single(recv, send, output_split_sizes=recv_splits, input_split_sizes=send_splits,
                                group=self.group)
@@ -121,8 +129,17 @@ class SlabDecomposition(object):
             layer = self.layer_of(x)
             li = torch.nonzero(layer == self.lay0).flatten()
             ri = torch.nonzero(layer == self.lay1 - 1).flatten()
-        idx = torch.cat([li, ri])
-        dest = torch.cat([torch.full_like(li, self.left), torch.full_like(ri, self.right)])
+        # rows grouped by destination rank, in rank order (what all_to_all_single sends)
+        parts = [(self.left, li), (self.right, ri)]
+        if self.right < self.left:
+            parts.reverse()
+        idx = torch.cat([parts[0][1], parts[1][1]])
+        # the CUDA path sends by counts (self._send_counts); the per-row destinations are for the generic exchange
+        dest = None if x.is_cuda else torch.cat([torch.full_like(parts[0][1], parts[0][0]),
+                                                 torch.full_like(parts[1][1], parts[1][0])])
+        self._send_counts = [0] * self.world
+        for rk, sel in parts:
+            self._send_counts[rk] += int(sel.shape[0])
         return idx, dest
 
     def halo_exchange(self, own):
@@ -243,13 +260,17 @@ class SlabSphEvaluator(object):
             dec._halo = None
             return 0
         idx, dest = dec.halo_select_x(S["r"][:no, 0])
-        ghosts, pattern = dec._exchange(self._pack(idx, S), dest)
+        L, st = _lib.load(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        rows = torch.empty((idx.shape[0], NCOL), dtype=torch.float64, device=self.device)
+        _lib.check(L.sph_halo_pack(P(idx), int(idx.shape[0]), P(S["r"]), P(S["v"]), P(S["m"]), P(S["h"]), P(S["t"]),
+                                   P(S["gid"]), P(rows), st), "sph_halo_pack")
+        ghosts, pattern = dec._exchange(rows, dest, send_counts=dec._send_counts)
         dec._halo = (idx, pattern)
         ng = int(ghosts.shape[0])
         self._reserve(no + ng, S)
-        S["r"][no:no + ng], S["v"][no:no + ng] = ghosts[:, C_R:C_R + 3], ghosts[:, C_V:C_V + 3]
-        S["m"][no:no + ng], S["h"][no:no + ng], S["t"][no:no + ng] = ghosts[:, C_M], ghosts[:, C_H], ghosts[:, C_T]
-        S["gid"][no:no + ng] = ghosts[:, C_GID].to(torch.int64)
+        _lib.check(L.sph_halo_unpack(P(ghosts), ng, no, P(S["r"]), P(S["v"]), P(S["m"]), P(S["h"]), P(S["t"]),
+                                     P(S["gid"]), st), "sph_halo_unpack")
         return ng
 
     def evaluate(self, timed=False, S=None):
@@ -282,9 +303,13 @@ class SlabSphEvaluator(object):
         if timed:
             ev[4].record()
         if ng:
-            pr = dec.halo_exchange_again([p[:no], rho[:no]])                         # B
-            p[no:] = pr[:, 0]
-            rho[no:] = pr[:, 1]
+            idx, pattern = dec._halo                                                 # B
+            L, st = _lib.load(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            P = lambda t: ctypes.c_void_p(t.data_ptr())
+            send = torch.empty((idx.shape[0], 2), dtype=torch.float64, device=self.device)
+            _lib.check(L.sph_halo_pack2(P(idx), int(idx.shape[0]), P(p), P(rho), P(send), st), "sph_halo_pack2")
+            pr, _ = dec._exchange(send, None, splits=pattern)
+            _lib.check(L.sph_halo_unpack2(P(pr), int(pr.shape[0]), no, P(p), P(rho), st), "sph_halo_unpack2")
             be.pressure_term(p, rho, no)                      # only the ghosts need their p/rho^2 refreshed
         if timed:
             ev[5].record()
