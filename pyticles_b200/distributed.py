@@ -200,7 +200,7 @@ class SlabSphEvaluator(object):
         vol = box[0] * box[1] * box[2]
         rl = (cutoff * cutoff + tol * tol) ** 0.5
         self.be.user_max_nbrs = int(1.35 * 4.18879 * rl ** 3 * self.n_total / vol) + 16
-        self.launches_per_eval = 15     # the 13 of one GPU + slab_select + pressure_term (ghosts)
+        self.launches_per_eval = 19     # the 13 of one GPU + slab_select, halo pack / unpack (x2), pressure_term (ghosts)
         self._events = []
         self.n_local = self.n_owned
 
