@@ -30,7 +30,61 @@
 #include "sph_device.cuh"
 #include "sph_tiles.cuh"
 
+// Compile-time tunables of the density / force passes (tools/variant_sweep.py builds and times variants):
+//   SPH_PP_BLOCK     threads per block            SPH_DENS_MINB / SPH_FORCE_MINB   __launch_bounds__ min blocks
+//   SPH_ROW_U / SPH_ROW_UF   neighbours gathered per pipeline stage (density / force)
+//   SPH_IDX_NOALLOC  1: neighbour-index loads bypass L1 allocation (the index stream is read once; the
+//                    gathered rows are what should stay resident)
+#ifndef SPH_PP_BLOCK
+#define SPH_PP_BLOCK 256
+#endif
+#ifndef SPH_DENS_MINB
+#define SPH_DENS_MINB 1
+#endif
+#ifndef SPH_FORCE_MINB
+#define SPH_FORCE_MINB 1
+#endif
+#ifndef SPH_ROW_U
+#define SPH_ROW_U 4
+#endif
+#ifndef SPH_ROW_UF
+#define SPH_ROW_UF 2
+#endif
+#ifndef SPH_IDX_NOALLOC
+#define SPH_IDX_NOALLOC 0
+#endif
+//   SPH_IDX_AHEAD    1 | 2: pipeline stages the neighbour indices are fetched ahead of their rows
+//   SPH_ROW_KEEP     1: gathered rows are loaded with L1::evict_last
+#ifndef SPH_IDX_AHEAD
+#define SPH_IDX_AHEAD 1
+#endif
+#ifndef SPH_ROW_KEEP
+#define SPH_ROW_KEEP 0
+#endif
+
 namespace {
+
+constexpr int kPPBlock = SPH_PP_BLOCK;
+
+__device__ __forceinline__ void load_row4(const double *p, double &a, double &b, double &c, double &d)
+{
+#if SPH_ROW_KEEP
+    asm volatile("ld.global.nc.L1::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#else
+    load4(p, a, b, c, d);
+#endif
+}
+
+__device__ __forceinline__ int load_idx(const int32_t *p)
+{
+#if SPH_IDX_NOALLOC
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
 
 
 __global__ void __launch_bounds__(kBlock)
@@ -413,7 +467,7 @@ __device__ __forceinline__ bool cell_is_interior(const sph_grid &, uint32_t flag
     return flag != 0u;       // computed once per particle by gather_kernel (rel4[., 3])
 }
 
-constexpr int kRowU = 4;             // neighbours gathered per pipeline stage
+constexpr int kRowU = SPH_ROW_U;             // neighbours gathered per pipeline stage
 
 template <bool UNIFORM_H, bool WRAP>
 __device__ __forceinline__ double density_row(const sph_grid &g, const double *__restrict__ pos4,
@@ -429,19 +483,30 @@ __device__ __forceinline__ double density_row(const sph_grid &g, const double *_
     // previous kRowU pairs are evaluated
     int jn[kRowU];
 #pragma unroll
-    for (int u = 0; u < kRowU; ++u) jn[u] = u < count ? row[(size_t)u * stride] : self;
+    for (int u = 0; u < kRowU; ++u) jn[u] = u < count ? load_idx(row + (size_t)u * stride) : self;
+#if SPH_IDX_AHEAD == 2
+    int jn2[kRowU];
+#pragma unroll
+    for (int u = 0; u < kRowU; ++u) jn2[u] = kRowU + u < count ? load_idx(row + (size_t)(kRowU + u) * stride) : self;
+#endif
     for (int k0 = 0; k0 < count; k0 += kRowU) {
         double bx[kRowU], by[kRowU], bz[kRowU], bm[kRowU];
         int j[kRowU];
 #pragma unroll
         for (int u = 0; u < kRowU; ++u) {
             j[u] = jn[u];
-            load4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
+            load_row4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
         }
 #pragma unroll
         for (int u = 0; u < kRowU; ++u) {
+#if SPH_IDX_AHEAD == 2
+            const int kn = k0 + 2 * kRowU + u;
+            jn[u] = jn2[u];
+            jn2[u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
+#else
             const int kn = k0 + kRowU + u;
-            jn[u] = kn < count ? row[(size_t)kn * stride] : self;
+            jn[u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
+#endif
         }
 #pragma unroll
         for (int u = 0; u < kRowU; ++u) {
@@ -475,7 +540,7 @@ __device__ __forceinline__ double density_row(const sph_grid &g, const double *_
 // contiguous in the sorted arrays) and the per-lane trip counts even out; the partial sums are
 // combined with shuffles.
 template <bool UNIFORM_H, int LPP>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kPPBlock, SPH_DENS_MINB)
 density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__restrict__ pos4,
                double *__restrict__ vel4, const float *__restrict__ rel4,
                const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
@@ -537,7 +602,7 @@ pressure_term_kernel(int n, int first_orig, const int32_t *__restrict__ perm, co
 
 struct ForceAcc { double ax, ay, az, du; };
 
-constexpr int kRowUF = 2;            // force: 8 doubles per neighbour, so a shorter stage
+constexpr int kRowUF = SPH_ROW_UF;            // force: 8 doubles per neighbour, so a shorter stage
 
 template <bool UNIFORM_H, bool WRAP>
 __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *__restrict__ pos4,
@@ -553,20 +618,31 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
     const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
     int jn[kRowUF];
 #pragma unroll
-    for (int u = 0; u < kRowUF; ++u) jn[u] = u < count ? row[(size_t)u * stride] : self;
+    for (int u = 0; u < kRowUF; ++u) jn[u] = u < count ? load_idx(row + (size_t)u * stride) : self;
+#if SPH_IDX_AHEAD == 2
+    int jn2[kRowUF];
+#pragma unroll
+    for (int u = 0; u < kRowUF; ++u) jn2[u] = kRowUF + u < count ? load_idx(row + (size_t)(kRowUF + u) * stride) : self;
+#endif
     for (int k0 = 0; k0 < count; k0 += kRowUF) {
         double bx[kRowUF], by[kRowUF], bz[kRowUF], bm[kRowUF], wx[kRowUF], wy[kRowUF], wz[kRowUF], Aj[kRowUF];
         int j[kRowUF];
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
             j[u] = jn[u];
-            load4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
-            load4(vel4 + 4 * (size_t)j[u], wx[u], wy[u], wz[u], Aj[u]);
+            load_row4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
+            load_row4(vel4 + 4 * (size_t)j[u], wx[u], wy[u], wz[u], Aj[u]);
         }
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
+#if SPH_IDX_AHEAD == 2
+            const int kn = k0 + 2 * kRowUF + u;
+            jn[u] = jn2[u];
+            jn2[u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
+#else
             const int kn = k0 + kRowUF + u;
-            jn[u] = kn < count ? row[(size_t)kn * stride] : self;
+            jn[u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
+#endif
         }
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
@@ -607,7 +683,7 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
 }
 
 template <bool UNIFORM_H, int LPP>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kPPBlock, SPH_FORCE_MINB)
 force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__restrict__ pos4,
              const double *__restrict__ vel4, const float *__restrict__ rel4,
              const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
@@ -1301,7 +1377,7 @@ int sph_density_eos(const sph_grid *g, const sph_buffers *b, const sph_eos *eos,
     cudaStream_t s = (cudaStream_t)stream;
     const int lpp = lanes_per_particle();
 #define SPH_LAUNCH_DENSITY(U, L)                                                                              \
-    density_kernel<U, L><<<blocks_for((int64_t)b->n * L, kBlock), kBlock, 0, s>>>(                            \
+    density_kernel<U, L><<<blocks_for((int64_t)b->n * L, kPPBlock), kPPBlock, 0, s>>>(                        \
         *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig, *eos, \
         list_fresh, use_hlr, d_rho, d_p, d_pco, d_u, d_t)
     if (h_uniform) {
@@ -1331,7 +1407,7 @@ int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, co
     const int lpp = lanes_per_particle();
 
 #define SPH_LAUNCH_FORCE(U, L)                                                                                 \
-    force_kernel<U, L><<<blocks_for((int64_t)b->n * L, kBlock), kBlock, 0, s>>>(                               \
+    force_kernel<U, L><<<blocks_for((int64_t)b->n * L, kPPBlock), kPPBlock, 0, s>>>(                           \
         *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig,        \
         list_fresh, fcutsq, dim, d_vdot, d_udot)
     if (h_uniform) {
