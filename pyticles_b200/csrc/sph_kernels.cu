@@ -53,13 +53,30 @@
 #ifndef SPH_IDX_NOALLOC
 #define SPH_IDX_NOALLOC 0
 #endif
-//   SPH_IDX_AHEAD    1 | 2: pipeline stages the neighbour indices are fetched ahead of their rows
+//   SPH_IDX_AHEAD / SPH_IDX_AHEAD_F   pipeline stages the neighbour indices are fetched ahead of their rows (density / force)
 //   SPH_ROW_KEEP     1: gathered rows are loaded with L1::evict_last
 #ifndef SPH_IDX_AHEAD
 #define SPH_IDX_AHEAD 1
 #endif
+#ifndef SPH_IDX_AHEAD_F
+#define SPH_IDX_AHEAD_F SPH_IDX_AHEAD
+#endif
 #ifndef SPH_ROW_KEEP
 #define SPH_ROW_KEEP 0
+#endif
+//   SPH_PP_SMQ       1: persistent blocks take chunks of kPPBlock particles from per-SM queues (%smid), so that the
+//                    blocks resident on one SM work on adjacent stretches of the Morton order and share gathered
+//                    rows in that SM's L1; an SM whose queue is empty steals from the others
+//   SPH_PP_MAXL1     1: ask for the largest L1 (shared-memory carve-out 0) for the density / force kernels
+//   SPH_ROW_PIPE     1: force pass requests the rows of the next stage before it evaluates the current one
+#ifndef SPH_ROW_PIPE
+#define SPH_ROW_PIPE 0
+#endif
+#ifndef SPH_PP_SMQ
+#define SPH_PP_SMQ 0
+#endif
+#ifndef SPH_PP_MAXL1
+#define SPH_PP_MAXL1 0
 #endif
 
 namespace {
@@ -72,6 +89,73 @@ __device__ __forceinline__ void load_row4(const double *p, double &a, double &b,
     asm volatile("ld.global.nc.L1::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
 #else
     load4(p, a, b, c, d);
+#endif
+}
+
+// Work distribution of the per-particle passes.  queue == nullptr: block b does chunk b.  Otherwise the grid
+// is persistent and chunk c belongs to queue c / per_queue; a block starts on the queue of the SM it runs on
+// and moves on to the next queue when one is drained, so every chunk is done exactly once wherever the blocks
+// land.  queue[] is zeroed before the launch.
+struct ChunkQueue {
+    uint32_t *queue;
+    int nq, per_queue, nchunks;
+};
+
+#if SPH_PP_SMQ
+__device__ __forceinline__ uint32_t sm_id()
+{
+    uint32_t v;
+    asm("mov.u32 %0, %%smid;" : "=r"(v));
+    return v;
+}
+
+// thread 0 only; the probe position lives in shared memory so that it costs no register in the pass itself
+__device__ __forceinline__ int chunk_grab(const ChunkQueue &cq, int &s_probe)
+{
+    const uint32_t home = sm_id() % (uint32_t)cq.nq;
+    int probe = s_probe;
+    int got = -1;
+    while (probe < cq.nq) {
+        uint32_t qi = home + (uint32_t)probe;
+        if (qi >= (uint32_t)cq.nq) qi -= (uint32_t)cq.nq;
+        const uint32_t c = atomicAdd(cq.queue + qi, 1u);
+        const long long chunk = (long long)qi * cq.per_queue + c;
+        if (c < (uint32_t)cq.per_queue && chunk < cq.nchunks) {
+            got = (int)chunk;
+            break;
+        }
+        ++probe;
+    }
+    s_probe = probe;
+    return got;
+}
+#endif
+
+template <class Body>
+__device__ __forceinline__ void for_each_chunk(const ChunkQueue &cq, Body body)
+{
+#if SPH_PP_SMQ
+    __shared__ int s_next, s_probe;
+    const bool queued = cq.queue != nullptr;
+    if (queued) {
+        if (threadIdx.x == 0) {
+            s_probe = 0;
+            s_next = chunk_grab(cq, s_probe);
+        }
+        __syncthreads();
+    }
+    for (;;) {
+        const int chunk = queued ? s_next : (int)blockIdx.x;
+        if (queued) __syncthreads();
+        if (chunk < 0) break;
+        if (queued && threadIdx.x == 0) s_next = chunk_grab(cq, s_probe);   // in flight while this chunk is worked on
+        body(chunk);
+        if (!queued) break;
+        __syncthreads();
+    }
+#else
+    (void)cq;
+    body((int)blockIdx.x);
 #endif
 }
 
@@ -481,32 +565,26 @@ __device__ __forceinline__ double density_row(const sph_grid &g, const double *_
     const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
     // indices are fetched one stage ahead, so that kRowU gathers are in flight while the
     // previous kRowU pairs are evaluated
-    int jn[kRowU];
+    int jn[SPH_IDX_AHEAD][kRowU];          // indices of the next SPH_IDX_AHEAD stages
 #pragma unroll
-    for (int u = 0; u < kRowU; ++u) jn[u] = u < count ? load_idx(row + (size_t)u * stride) : self;
-#if SPH_IDX_AHEAD == 2
-    int jn2[kRowU];
+    for (int st = 0; st < SPH_IDX_AHEAD; ++st)
 #pragma unroll
-    for (int u = 0; u < kRowU; ++u) jn2[u] = kRowU + u < count ? load_idx(row + (size_t)(kRowU + u) * stride) : self;
-#endif
+        for (int u = 0; u < kRowU; ++u)
+            jn[st][u] = st * kRowU + u < count ? load_idx(row + (size_t)(st * kRowU + u) * stride) : self;
     for (int k0 = 0; k0 < count; k0 += kRowU) {
         double bx[kRowU], by[kRowU], bz[kRowU], bm[kRowU];
         int j[kRowU];
 #pragma unroll
         for (int u = 0; u < kRowU; ++u) {
-            j[u] = jn[u];
+            j[u] = jn[0][u];
             load_row4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
         }
 #pragma unroll
         for (int u = 0; u < kRowU; ++u) {
-#if SPH_IDX_AHEAD == 2
-            const int kn = k0 + 2 * kRowU + u;
-            jn[u] = jn2[u];
-            jn2[u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
-#else
-            const int kn = k0 + kRowU + u;
-            jn[u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
-#endif
+            const int kn = k0 + SPH_IDX_AHEAD * kRowU + u;
+#pragma unroll
+            for (int st = 0; st + 1 < SPH_IDX_AHEAD; ++st) jn[st][u] = jn[st + 1][u];
+            jn[SPH_IDX_AHEAD - 1][u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
         }
 #pragma unroll
         for (int u = 0; u < kRowU; ++u) {
@@ -547,9 +625,10 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
                const int32_t *__restrict__ cnt, const sph_status *__restrict__ status,
                const double *__restrict__ h_orig, sph_eos eos, int list_fresh, int long_range,
                double *__restrict__ rho_out, double *__restrict__ p_out, double *__restrict__ pco_out,
-               double *__restrict__ u_out, double *__restrict__ t_io)
+               double *__restrict__ u_out, double *__restrict__ t_io, ChunkQueue cq)
 {
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    for_each_chunk(cq, [&](int chunk) {
+    const int gt = chunk * kPPBlock + threadIdx.x;
     const int a = gt / LPP, q = gt % LPP;
     const bool active = a < n;
     double ax = 0, ay = 0, az = 0, am = 0;
@@ -586,6 +665,7 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
     u_out[orig] = u;
     t_io[orig] = (u + eos.adash * rho) / eos.kbdash;                        // properties.py:49,120
     vel4[4 * (size_t)a + 3] = p / (rho * rho);                              // forces.py:353 operand
+    });
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -616,34 +696,63 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
 {
     ForceAcc f = {0.0, 0.0, 0.0, 0.0};
     const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
-    int jn[kRowUF];
+#if SPH_ROW_PIPE
+    // double-buffered rows: the rows of stage k0 + kRowUF are requested before stage k0 is evaluated
+    int jn[SPH_IDX_AHEAD_F][kRowUF];          // indices of the stages after the one whose rows are in flight
+    double bx[kRowUF], by[kRowUF], bz[kRowUF], bm[kRowUF], wx[kRowUF], wy[kRowUF], wz[kRowUF], Aj[kRowUF];
+    int j[kRowUF];
 #pragma unroll
-    for (int u = 0; u < kRowUF; ++u) jn[u] = u < count ? load_idx(row + (size_t)u * stride) : self;
-#if SPH_IDX_AHEAD == 2
-    int jn2[kRowUF];
+    for (int u = 0; u < kRowUF; ++u) j[u] = u < count ? load_idx(row + (size_t)u * stride) : self;
 #pragma unroll
-    for (int u = 0; u < kRowUF; ++u) jn2[u] = kRowUF + u < count ? load_idx(row + (size_t)(kRowUF + u) * stride) : self;
-#endif
+    for (int st = 0; st < SPH_IDX_AHEAD_F; ++st)
+#pragma unroll
+        for (int u = 0; u < kRowUF; ++u)
+            jn[st][u] = (st + 1) * kRowUF + u < count ? load_idx(row + (size_t)((st + 1) * kRowUF + u) * stride) : self;
+#pragma unroll
+    for (int u = 0; u < kRowUF; ++u) {
+        load_row4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
+        load_row4(vel4 + 4 * (size_t)j[u], wx[u], wy[u], wz[u], Aj[u]);
+    }
+    for (int k0 = 0; k0 < count; k0 += kRowUF) {
+        double nbx[kRowUF], nby[kRowUF], nbz[kRowUF], nbm[kRowUF], nwx[kRowUF], nwy[kRowUF], nwz[kRowUF], nAj[kRowUF];
+        int nj[kRowUF];
+#pragma unroll
+        for (int u = 0; u < kRowUF; ++u) {
+            nj[u] = jn[0][u];
+            load_row4(pos4 + 4 * (size_t)nj[u], nbx[u], nby[u], nbz[u], nbm[u]);
+            load_row4(vel4 + 4 * (size_t)nj[u], nwx[u], nwy[u], nwz[u], nAj[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kRowUF; ++u) {
+            const int kn = k0 + (SPH_IDX_AHEAD_F + 1) * kRowUF + u;
+#pragma unroll
+            for (int st = 0; st + 1 < SPH_IDX_AHEAD_F; ++st) jn[st][u] = jn[st + 1][u];
+            jn[SPH_IDX_AHEAD_F - 1][u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
+        }
+#else
+    int jn[SPH_IDX_AHEAD_F][kRowUF];          // indices of the next SPH_IDX_AHEAD_F stages
+#pragma unroll
+    for (int st = 0; st < SPH_IDX_AHEAD_F; ++st)
+#pragma unroll
+        for (int u = 0; u < kRowUF; ++u)
+            jn[st][u] = st * kRowUF + u < count ? load_idx(row + (size_t)(st * kRowUF + u) * stride) : self;
     for (int k0 = 0; k0 < count; k0 += kRowUF) {
         double bx[kRowUF], by[kRowUF], bz[kRowUF], bm[kRowUF], wx[kRowUF], wy[kRowUF], wz[kRowUF], Aj[kRowUF];
         int j[kRowUF];
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
-            j[u] = jn[u];
+            j[u] = jn[0][u];
             load_row4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
             load_row4(vel4 + 4 * (size_t)j[u], wx[u], wy[u], wz[u], Aj[u]);
         }
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
-#if SPH_IDX_AHEAD == 2
-            const int kn = k0 + 2 * kRowUF + u;
-            jn[u] = jn2[u];
-            jn2[u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
-#else
-            const int kn = k0 + kRowUF + u;
-            jn[u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
-#endif
+            const int kn = k0 + SPH_IDX_AHEAD_F * kRowUF + u;
+#pragma unroll
+            for (int st = 0; st + 1 < SPH_IDX_AHEAD_F; ++st) jn[st][u] = jn[st + 1][u];
+            jn[SPH_IDX_AHEAD_F - 1][u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
         }
+#endif
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
             // Pair (i<j in original order) contributes +a to i and -a to j with dr = r_j - r_i.
@@ -678,6 +787,14 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
                 f.du += (0.5 * dot) * bm[u];
             }
         }
+#if SPH_ROW_PIPE
+#pragma unroll
+        for (int u = 0; u < kRowUF; ++u) {
+            j[u] = nj[u];
+            bx[u] = nbx[u]; by[u] = nby[u]; bz[u] = nbz[u]; bm[u] = nbm[u];
+            wx[u] = nwx[u]; wy[u] = nwy[u]; wz[u] = nwz[u]; Aj[u] = nAj[u];
+        }
+#endif
     }
     return f;
 }
@@ -689,9 +806,10 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
              const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
              const int32_t *__restrict__ cnt, const sph_status *__restrict__ status,
              const double *__restrict__ h_orig, int list_fresh, double fcutsq, int dim,
-             double *__restrict__ vdot, double *__restrict__ udot)
+             double *__restrict__ vdot, double *__restrict__ udot, ChunkQueue cq)
 {
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    for_each_chunk(cq, [&](int chunk) {
+    const int gt = chunk * kPPBlock + threadIdx.x;
     const int a = gt / LPP, q = gt % LPP;
     const bool active = a < n;
     double px = 0, py = 0, pz = 0, pm = 0, vx = 0, vy = 0, vz = 0, Ai = 0;
@@ -727,6 +845,7 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
     vdot[3 * (size_t)orig + 1] += f.ay;
     vdot[3 * (size_t)orig + 2] += f.az;
     udot[orig] += f.du;
+    });
 }
 
 // ------------------------------------------------------------------ heat conduction (c_forces.pyx:196-239)
@@ -1140,6 +1259,46 @@ int sm_count()
     return g_sm_count;
 }
 
+constexpr int kQueueSlots = 1024;     // uint32 slots at the head of sph_buffers.scan_tmp (free after the cell scan)
+
+// Launch geometry of a per-particle pass.  Default: one block per chunk of kPPBlock lanes.  With SPH_PP_SMQ the
+// grid is persistent (resident blocks per SM x SMs) and the chunks are dealt to per-SM queues kept in scan_tmp.
+ChunkQueue chunk_plan(const sph_buffers *b, int lpp, const void *kernel, cudaStream_t s, int &grid)
+{
+    ChunkQueue cq = {nullptr, 0, 0, 0};
+    cq.nchunks = blocks_for((int64_t)b->n * lpp, kPPBlock);
+    grid = cq.nchunks;
+#if SPH_PP_MAXL1
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+#endif
+#if SPH_PP_SMQ
+    const int nsm = sm_count();
+    static const void *seen[32];
+    static int seen_blocks[32], n_seen = 0;
+    int per_sm = 0;
+    for (int i = 0; i < n_seen; ++i)
+        if (seen[i] == kernel) per_sm = seen_blocks[i];
+    if (!per_sm) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPPBlock, 0);
+        if (per_sm > 0 && n_seen < 32) {
+            seen[n_seen] = kernel;
+            seen_blocks[n_seen++] = per_sm;
+        }
+    }
+    if (b->scan_tmp && nsm <= kQueueSlots && per_sm > 0 && cq.nchunks > 2 * nsm * per_sm) {
+        cq.queue = b->scan_tmp;
+        cq.nq = nsm;
+        cq.per_queue = (cq.nchunks + nsm - 1) / nsm;
+        grid = nsm * per_sm;
+        cudaMemsetAsync(cq.queue, 0, sizeof(uint32_t) * (size_t)nsm, s);
+    }
+#else
+    (void)kernel;
+    (void)s;
+#endif
+    return cq;
+}
+
 }  // namespace
 
 // ====================================================================== C ABI
@@ -1149,7 +1308,7 @@ const char *sph_version(void) { return "pyticles_b200 0.2 (sm_100a, abi 2)"; }
 
 int64_t sph_scan_tmp_elems(uint32_t ncode)
 {
-    return ((int64_t)ncode + kScanTile - 1) / kScanTile + 2;
+    return ((int64_t)ncode + kScanTile - 1) / kScanTile + 2 + kQueueSlots;
 }
 
 int64_t sph_nbr_elems(int32_t n, int32_t max_nbrs)
@@ -1377,9 +1536,13 @@ int sph_density_eos(const sph_grid *g, const sph_buffers *b, const sph_eos *eos,
     cudaStream_t s = (cudaStream_t)stream;
     const int lpp = lanes_per_particle();
 #define SPH_LAUNCH_DENSITY(U, L)                                                                              \
-    density_kernel<U, L><<<blocks_for((int64_t)b->n * L, kPPBlock), kPPBlock, 0, s>>>(                        \
-        *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig, *eos, \
-        list_fresh, use_hlr, d_rho, d_p, d_pco, d_u, d_t)
+    do {                                                                                                         \
+        int grid = 0;                                                                                         \
+        const ChunkQueue cq = chunk_plan(b, L, (const void *)density_kernel<U, L>, s, grid);                  \
+        density_kernel<U, L><<<grid, kPPBlock, 0, s>>>(                                                       \
+            *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig,   \
+            *eos, list_fresh, use_hlr, d_rho, d_p, d_pco, d_u, d_t, cq);                                      \
+    } while (0)
     if (h_uniform) {
         if (lpp == 1) SPH_LAUNCH_DENSITY(true, 1);
         else if (lpp == 2) SPH_LAUNCH_DENSITY(true, 2);
@@ -1407,9 +1570,13 @@ int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, co
     const int lpp = lanes_per_particle();
 
 #define SPH_LAUNCH_FORCE(U, L)                                                                                 \
-    force_kernel<U, L><<<blocks_for((int64_t)b->n * L, kPPBlock), kPPBlock, 0, s>>>(                           \
-        *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig,        \
-        list_fresh, fcutsq, dim, d_vdot, d_udot)
+    do {                                                                                                          \
+        int grid = 0;                                                                                          \
+        const ChunkQueue cq = chunk_plan(b, L, (const void *)force_kernel<U, L>, s, grid);                     \
+        force_kernel<U, L><<<grid, kPPBlock, 0, s>>>(                                                          \
+            *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig,    \
+            list_fresh, fcutsq, dim, d_vdot, d_udot, cq);                                                      \
+    } while (0)
     if (h_uniform) {
         if (lpp == 1) SPH_LAUNCH_FORCE(true, 1);
         else if (lpp == 2) SPH_LAUNCH_FORCE(true, 2);

@@ -1,11 +1,9 @@
 #!/bin/bash
 # One gpurun call: variant sweep of the density/force passes -> GPU test suite and full bench line on the winner.
-#   /usr/local/graft/bin/gpurun --timeout 840 -- 'bash tools/gpu_call_r1f.sh'
+#   /usr/local/graft/bin/gpurun --timeout 840 -- 'bash tools/gpu_call_r1f.sh <variant names>'
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/r1f_gpu.txt 2>&1
-timeout 420 python tools/variant_sweep.py run base noalloc b128_r72_80 ahead2 b128 keep u4_uf1_b128_r72_72_ahead2 \
-    b128_r72_80_noalloc_ahead2 u2_uf1_b128_r48_72 b128_r64_64 noalloc_keep u6_uf3 b64 b512 --budget=330 \
-    > gpurun_out/r1f_sweep.log 2>&1
+timeout 420 python tools/variant_sweep.py run "$@" --budget=300 > gpurun_out/r1f_sweep.log 2>&1
 W=$(cat gpurun_out/variant_winner.txt 2>/dev/null || echo base)
 export PYTICLES_B200_LIB=$PWD/variants/libpyticles_b200_$W.so
 echo "winner $W" | tee gpurun_out/r1f_winner.txt

@@ -38,6 +38,20 @@ VARIANTS = {
     "b512": ["-DSPH_PP_BLOCK=512"],
     "b64": ["-DSPH_PP_BLOCK=64"],
 }
+# second generation: on top of the first sweep's winner (profiles/r1f_variant_sweep.txt)
+W = ["-DSPH_ROW_UF=1", "-DSPH_PP_BLOCK=128", "-DSPH_DENS_MINB=7", "-DSPH_FORCE_MINB=7", "-DSPH_IDX_AHEAD=2"]
+W_NOF = [f for f in W if "FORCE_MINB" not in f]
+VARIANTS.update({
+    "w": W,
+    "w_smq": W + ["-DSPH_PP_SMQ=1"],
+    "w_smq_maxl1": W + ["-DSPH_PP_SMQ=1", "-DSPH_PP_MAXL1=1"],
+    "w_maxl1": W + ["-DSPH_PP_MAXL1=1"],
+    "w_f_ahead3": W + ["-DSPH_IDX_AHEAD_F=3"],
+    "w_f_ahead4": W + ["-DSPH_IDX_AHEAD_F=4"],
+    "w_f_pipe_r80": W_NOF + ["-DSPH_FORCE_MINB=6", "-DSPH_ROW_PIPE=1"],
+    "w_f_r64": W_NOF + ["-DSPH_FORCE_MINB=8"],
+    "base_smq": ["-DSPH_PP_SMQ=1"],
+})
 
 
 def lib_path(name):
