@@ -30,45 +30,49 @@
 #include "sph_device.cuh"
 #include "sph_tiles.cuh"
 
-// Compile-time tunables of the density / force passes (tools/variant_sweep.py builds and times variants):
+// Compile-time tunables of the density / force passes.  tools/variant_sweep.py builds one library per setting
+// and times them on the bench workload; the defaults are the fastest of those sweeps on B200 (256^3 box,
+// profiles/r1f_variant_sweep_gen*.txt): 128-thread blocks capped at 72 registers (7 blocks = 28 warps per SM
+// instead of 24 / 16), the force pass gathering one neighbour per stage instead of two, indices fetched two
+// stages ahead.  Every setting evaluates a particle's row in the same order: the results are bit-identical.
 //   SPH_PP_BLOCK     threads per block            SPH_DENS_MINB / SPH_FORCE_MINB   __launch_bounds__ min blocks
 //   SPH_ROW_U / SPH_ROW_UF   neighbours gathered per pipeline stage (density / force)
-//   SPH_IDX_NOALLOC  1: neighbour-index loads bypass L1 allocation (the index stream is read once; the
-//                    gathered rows are what should stay resident)
+//   SPH_IDX_AHEAD / SPH_IDX_AHEAD_F   pipeline stages the neighbour indices are fetched ahead of their rows
+//   SPH_IDX_NOALLOC  1: neighbour-index loads bypass L1 allocation      (measured: no effect)
+//   SPH_ROW_KEEP     1: gathered rows are loaded with L1::evict_last    (measured: no effect)
+//   SPH_ROW_PIPE     1: force pass requests the rows of the next stage before it evaluates the current one
+//                    (measured: slower, the second row buffer spills under the register cap)
+//   SPH_PP_SMQ       1: persistent blocks take chunks of kPPBlock particles from per-SM queues (%smid), so that the
+//                    blocks resident on one SM work on adjacent stretches of the Morton order and share gathered
+//                    rows in that SM's L1; an SM whose queue is empty steals from the others (measured: 3 % slower)
+//   SPH_PP_MAXL1     1: ask for the largest L1 (shared-memory carve-out 0)    (measured: no effect)
 #ifndef SPH_PP_BLOCK
-#define SPH_PP_BLOCK 256
+#define SPH_PP_BLOCK 128
 #endif
 #ifndef SPH_DENS_MINB
-#define SPH_DENS_MINB 1
+#define SPH_DENS_MINB 7
 #endif
 #ifndef SPH_FORCE_MINB
-#define SPH_FORCE_MINB 1
+#define SPH_FORCE_MINB 7
 #endif
 #ifndef SPH_ROW_U
 #define SPH_ROW_U 4
 #endif
 #ifndef SPH_ROW_UF
-#define SPH_ROW_UF 2
+#define SPH_ROW_UF 1
 #endif
-#ifndef SPH_IDX_NOALLOC
-#define SPH_IDX_NOALLOC 0
-#endif
-//   SPH_IDX_AHEAD / SPH_IDX_AHEAD_F   pipeline stages the neighbour indices are fetched ahead of their rows (density / force)
-//   SPH_ROW_KEEP     1: gathered rows are loaded with L1::evict_last
 #ifndef SPH_IDX_AHEAD
-#define SPH_IDX_AHEAD 1
+#define SPH_IDX_AHEAD 2
 #endif
 #ifndef SPH_IDX_AHEAD_F
 #define SPH_IDX_AHEAD_F SPH_IDX_AHEAD
 #endif
+#ifndef SPH_IDX_NOALLOC
+#define SPH_IDX_NOALLOC 0
+#endif
 #ifndef SPH_ROW_KEEP
 #define SPH_ROW_KEEP 0
 #endif
-//   SPH_PP_SMQ       1: persistent blocks take chunks of kPPBlock particles from per-SM queues (%smid), so that the
-//                    blocks resident on one SM work on adjacent stretches of the Morton order and share gathered
-//                    rows in that SM's L1; an SM whose queue is empty steals from the others
-//   SPH_PP_MAXL1     1: ask for the largest L1 (shared-memory carve-out 0) for the density / force kernels
-//   SPH_ROW_PIPE     1: force pass requests the rows of the next stage before it evaluates the current one
 #ifndef SPH_ROW_PIPE
 #define SPH_ROW_PIPE 0
 #endif
@@ -683,6 +687,7 @@ pressure_term_kernel(int n, int first_orig, const int32_t *__restrict__ perm, co
 struct ForceAcc { double ax, ay, az, du; };
 
 constexpr int kRowUF = SPH_ROW_UF;            // force: 8 doubles per neighbour, so a shorter stage
+constexpr int kRowUC = 2;                     // conduction (not register-capped)
 
 template <bool UNIFORM_H, bool WRAP>
 __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *__restrict__ pos4,
@@ -871,25 +876,25 @@ __device__ __forceinline__ double conduction_row(const sph_grid &g, const double
 {
     double acc = 0.0;
     const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
-    int jn[kRowUF];
+    int jn[kRowUC];
 #pragma unroll
-    for (int u = 0; u < kRowUF; ++u) jn[u] = u < count ? row[(size_t)u * 32] : self;
-    for (int k0 = 0; k0 < count; k0 += kRowUF) {
-        double bx[kRowUF], by[kRowUF], bz[kRowUF], bm[kRowUF], ex[kRowUF], ey[kRowUF], ez[kRowUF], ew[kRowUF];
-        int j[kRowUF];
+    for (int u = 0; u < kRowUC; ++u) jn[u] = u < count ? row[(size_t)u * 32] : self;
+    for (int k0 = 0; k0 < count; k0 += kRowUC) {
+        double bx[kRowUC], by[kRowUC], bz[kRowUC], bm[kRowUC], ex[kRowUC], ey[kRowUC], ez[kRowUC], ew[kRowUC];
+        int j[kRowUC];
 #pragma unroll
-        for (int u = 0; u < kRowUF; ++u) {
+        for (int u = 0; u < kRowUC; ++u) {
             j[u] = jn[u];
             load4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
             load4(aux4 + 4 * (size_t)j[u], ex[u], ey[u], ez[u], ew[u]);
         }
 #pragma unroll
-        for (int u = 0; u < kRowUF; ++u) {
-            const int kn = k0 + kRowUF + u;
+        for (int u = 0; u < kRowUC; ++u) {
+            const int kn = k0 + kRowUC + u;
             jn[u] = kn < count ? row[(size_t)kn * 32] : self;
         }
 #pragma unroll
-        for (int u = 0; u < kRowUF; ++u) {
+        for (int u = 0; u < kRowUC; ++u) {
             double dx = bx[u] - px, dy = by[u] - py, dz = bz[u] - pz;
             if (WRAP) {
                 dx = min_image(dx, g.box[0], hx);

@@ -19,39 +19,45 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "variants")
 
+R1E = dict(SPH_PP_BLOCK=256, SPH_DENS_MINB=1, SPH_FORCE_MINB=1, SPH_ROW_U=4, SPH_ROW_UF=2, SPH_IDX_AHEAD=1)   # defaults up to r1e
+W = dict(SPH_PP_BLOCK=128, SPH_DENS_MINB=7, SPH_FORCE_MINB=7, SPH_ROW_U=4, SPH_ROW_UF=1, SPH_IDX_AHEAD=2)     # defaults since r1f
+
+
+def _v(base, **kw):
+    d = dict(base)
+    d.update(kw)
+    return ["-D%s=%s" % kv for kv in sorted(d.items())]
+
+
 VARIANTS = {
-    "base": [],
-    "noalloc": ["-DSPH_IDX_NOALLOC=1"],
-    "keep": ["-DSPH_ROW_KEEP=1"],
-    "noalloc_keep": ["-DSPH_IDX_NOALLOC=1", "-DSPH_ROW_KEEP=1"],
-    "ahead2": ["-DSPH_IDX_AHEAD=2"],
-    "b128": ["-DSPH_PP_BLOCK=128"],
-    "b128_r72_80": ["-DSPH_PP_BLOCK=128", "-DSPH_DENS_MINB=7", "-DSPH_FORCE_MINB=6"],
-    "b128_r64_64": ["-DSPH_PP_BLOCK=128", "-DSPH_DENS_MINB=8", "-DSPH_FORCE_MINB=8"],
-    "u2_uf1_b128_r48_72": ["-DSPH_ROW_U=2", "-DSPH_ROW_UF=1", "-DSPH_PP_BLOCK=128", "-DSPH_DENS_MINB=10",
-                           "-DSPH_FORCE_MINB=7"],
-    "u4_uf1_b128_r72_72_ahead2": ["-DSPH_ROW_UF=1", "-DSPH_PP_BLOCK=128", "-DSPH_DENS_MINB=7", "-DSPH_FORCE_MINB=7",
-                                  "-DSPH_IDX_AHEAD=2"],
-    "u6_uf3": ["-DSPH_ROW_U=6", "-DSPH_ROW_UF=3"],
-    "b128_r72_80_noalloc_ahead2": ["-DSPH_PP_BLOCK=128", "-DSPH_DENS_MINB=7", "-DSPH_FORCE_MINB=6",
-                                   "-DSPH_IDX_NOALLOC=1", "-DSPH_IDX_AHEAD=2"],
-    "b512": ["-DSPH_PP_BLOCK=512"],
-    "b64": ["-DSPH_PP_BLOCK=64"],
+    "default": [],
+    # first sweep (profiles/r1f_variant_sweep_gen1.txt): around the r1e defaults
+    "base": _v(R1E),
+    "noalloc": _v(R1E, SPH_IDX_NOALLOC=1),
+    "keep": _v(R1E, SPH_ROW_KEEP=1),
+    "noalloc_keep": _v(R1E, SPH_IDX_NOALLOC=1, SPH_ROW_KEEP=1),
+    "ahead2": _v(R1E, SPH_IDX_AHEAD=2),
+    "b128": _v(R1E, SPH_PP_BLOCK=128),
+    "b128_r72_80": _v(R1E, SPH_PP_BLOCK=128, SPH_DENS_MINB=7, SPH_FORCE_MINB=6),
+    "b128_r64_64": _v(R1E, SPH_PP_BLOCK=128, SPH_DENS_MINB=8, SPH_FORCE_MINB=8),
+    "u2_uf1_b128_r48_72": _v(R1E, SPH_ROW_U=2, SPH_ROW_UF=1, SPH_PP_BLOCK=128, SPH_DENS_MINB=10, SPH_FORCE_MINB=7),
+    "u4_uf1_b128_r72_72_ahead2": _v(W),
+    "u6_uf3": _v(R1E, SPH_ROW_U=6, SPH_ROW_UF=3),
+    "b128_r72_80_noalloc_ahead2": _v(R1E, SPH_PP_BLOCK=128, SPH_DENS_MINB=7, SPH_FORCE_MINB=6, SPH_IDX_NOALLOC=1,
+                                     SPH_IDX_AHEAD=2),
+    "b512": _v(R1E, SPH_PP_BLOCK=512),
+    "b64": _v(R1E, SPH_PP_BLOCK=64),
+    # second sweep (profiles/r1f_variant_sweep_gen2.txt): on top of the first sweep's winner
+    "w": _v(W),
+    "w_smq": _v(W, SPH_PP_SMQ=1),
+    "w_smq_maxl1": _v(W, SPH_PP_SMQ=1, SPH_PP_MAXL1=1),
+    "w_maxl1": _v(W, SPH_PP_MAXL1=1),
+    "w_f_ahead3": _v(W, SPH_IDX_AHEAD_F=3),
+    "w_f_ahead4": _v(W, SPH_IDX_AHEAD_F=4),
+    "w_f_pipe_r80": _v(W, SPH_FORCE_MINB=6, SPH_ROW_PIPE=1),
+    "w_f_r64": _v(W, SPH_FORCE_MINB=8),
+    "base_smq": _v(R1E, SPH_PP_SMQ=1),
 }
-# second generation: on top of the first sweep's winner (profiles/r1f_variant_sweep.txt)
-W = ["-DSPH_ROW_UF=1", "-DSPH_PP_BLOCK=128", "-DSPH_DENS_MINB=7", "-DSPH_FORCE_MINB=7", "-DSPH_IDX_AHEAD=2"]
-W_NOF = [f for f in W if "FORCE_MINB" not in f]
-VARIANTS.update({
-    "w": W,
-    "w_smq": W + ["-DSPH_PP_SMQ=1"],
-    "w_smq_maxl1": W + ["-DSPH_PP_SMQ=1", "-DSPH_PP_MAXL1=1"],
-    "w_maxl1": W + ["-DSPH_PP_MAXL1=1"],
-    "w_f_ahead3": W + ["-DSPH_IDX_AHEAD_F=3"],
-    "w_f_ahead4": W + ["-DSPH_IDX_AHEAD_F=4"],
-    "w_f_pipe_r80": W_NOF + ["-DSPH_FORCE_MINB=6", "-DSPH_ROW_PIPE=1"],
-    "w_f_r64": W_NOF + ["-DSPH_FORCE_MINB=8"],
-    "base_smq": ["-DSPH_PP_SMQ=1"],
-})
 
 
 def lib_path(name):
