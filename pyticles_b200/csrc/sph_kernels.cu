@@ -1235,6 +1235,29 @@ inline int launch_status()
     return e == cudaSuccess ? SPH_OK : (int)e;
 }
 
+// Diagnostic (SPH_SORT_ROWS=1 in the environment): rewrite every ELL row in ascending order of the sorted
+// neighbour index after the neighbour pass, to measure what a common sweep order of the lanes of a warp is
+// worth to the gathers of the density / force passes.  Not tuned: one thread per row, local-memory sort.
+__global__ void __launch_bounds__(kBlock)
+row_sort_kernel(int n, int K, int32_t *__restrict__ nbr, const int32_t *__restrict__ cnt)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const int c = min(cnt[a], K);
+    constexpr int kMax = 96;
+    if (c < 2 || c > kMax) return;
+    int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
+    int32_t v[kMax];
+    for (int k = 0; k < c; ++k) v[k] = row[(size_t)k * 32];
+    for (int i = 1; i < c; ++i) {
+        const int32_t x = v[i];
+        int j = i - 1;
+        while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; }
+        v[j + 1] = x;
+    }
+    for (int k = 0; k < c; ++k) row[(size_t)k * 32] = v[k];
+}
+
 // Lanes cooperating on one particle in the density / force passes.  Measured on B200 (256^3):
 // 1 lane per particle is fastest (density 2.10 ms; 2 lanes 2.52, 4 lanes 3.69, 8 lanes 5.23):
 // splitting a row over lanes makes the index loads touch LPP lines per request and buys nothing
@@ -1528,7 +1551,15 @@ int sph_nlist_build(const sph_grid *g, const sph_buffers *b, void *stream)
         const int rc = sph_tiles::launch_list(g, b, s);
         if (rc != SPH_OK) return rc;
     }
-    return nlist_general(g, b, tiles ? 1 : 0, s);
+    const int rc = nlist_general(g, b, tiles ? 1 : 0, s);
+    static int sort_rows = -1;
+    if (sort_rows < 0) {
+        const char *e = getenv("SPH_SORT_ROWS");
+        sort_rows = e ? atoi(e) : 0;
+    }
+    if (rc == SPH_OK && sort_rows)
+        row_sort_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, s>>>(b->n, b->max_nbrs, b->nbr, b->cnt);
+    return rc;
 }
 
 int sph_density_eos(const sph_grid *g, const sph_buffers *b, const sph_eos *eos,
