@@ -1287,6 +1287,7 @@ int sm_count()
     return g_sm_count;
 }
 
+constexpr double kCellTarget = 8.0;    // particles per cell the planner widens sparse grids towards (0: off)
 constexpr int kQueueSlots = 1024;     // uint32 slots at the head of sph_buffers.scan_tmp (free after the cell scan)
 
 // Launch geometry of a per-particle pass.  Default: one block per chunk of kPPBlock lanes.  With SPH_PP_SMQ the
@@ -1429,6 +1430,40 @@ int sph_grid_plan(const double box[3], double cutoff, double tolerance, int64_t 
             }
             if (best < 0) break;
             g->nc[best] = g->nc[best] / 2 < 3 ? 3 : g->nc[best] / 2;
+        }
+    }
+    // Few particles per cell: the neighbour pass pays its per-cell work (window staging, scans, row write-out) for
+    // too few particles -- a 256^3 box at cutoff 1.5 (3.4 per cell) builds slower than at cutoff 2 (8 per cell) although
+    // it tests fewer candidates (profiles/r1e_nl_sweep.txt).  Widen the cells of the occupied dimensions towards
+    // kCellTarget particles per cell; any width >= the list radius keeps the cells a superset filter.
+    // SPH_CELL_TARGET in the environment overrides the target (0: always the narrowest cells).
+    if (n_hint > 0) {
+        static double target = -1.0;
+        if (target < 0.0) {
+            const char *e = getenv("SPH_CELL_TARGET");
+            target = e ? atof(e) : kCellTarget;
+            if (!(target >= 0.0) || target > 64.0) target = kCellTarget;
+        }
+        double occ[3], cells = 1.0;
+        int wide = 0;
+        for (int d = 0; d < 3; ++d) {
+            occ[d] = g->nc[d];
+            if (occ_lo && occ_hi) {
+                occ[d] = floor((occ_hi[d] - occ_lo[d]) / (box[d] / g->nc[d])) + 1.0;
+                if (!(occ[d] >= 1.0)) occ[d] = 1.0;
+                if (occ[d] > g->nc[d]) occ[d] = g->nc[d];
+            }
+            cells *= occ[d];
+            if (occ[d] >= 4.0) ++wide;
+        }
+        const double mean = (double)n_hint / cells;
+        if (target > 0.0 && wide > 0 && mean < 0.625 * target) {
+            const double f = pow(mean / target, 1.0 / wide);
+            for (int d = 0; d < 3; ++d) {
+                if (occ[d] < 4.0) continue;
+                int nc = (int)floor(g->nc[d] * f);
+                g->nc[d] = nc < 3 ? 3 : nc;
+            }
         }
     }
     double wmax = 0.0;

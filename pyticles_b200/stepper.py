@@ -22,8 +22,8 @@ class SphEvaluator(object):
     kernel_names = {"cells+reorder": "bin_kernel+scan+scatter_kernel+cell_sort_kernel+gather_kernel",
                     "neighbour": "tile_list_kernel", "density": "density_kernel<true>", "force": "force_kernel<true>"}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` on the c3 workload
-    # (profiles/r1e_kernels.txt); only meaningful for that workload
-    ncu_traffic = {"cells+reorder": None, "neighbour": 2.65e9, "density": 5.04e9, "force": 4.91e9}
+    # (profiles/r1f_kernels.txt); only meaningful for that workload
+    ncu_traffic = {"cells+reorder": None, "neighbour": 2.65e9, "density": 5.04e9, "force": 4.92e9}
 
     def __init__(self, p, nl, force, eos=(2.0, 0.5, 1.0)):
         self.p, self.nl, self.force, self.eos = p, nl, force, eos

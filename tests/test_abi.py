@@ -73,9 +73,27 @@ def test_grid_plan_cells_cover_list_radius(lib):
 def test_grid_plan_coarsens_empty_dimension(lib):
     rc, g = _plan(lib, (1024., 1024., 1024.), 2.0, 0.0, 1 << 20, (0.4, 0.4, 0.4), (1023.6, 1023.6, 0.6))
     assert rc == 0
-    assert g.nc[0] == g.nc[1] == 511 or g.nc[0] == g.nc[1] == 512
+    # the sheet has 4 particles per narrowest cell: x and y are widened towards 8 per cell, z is coarsened
+    assert g.nc[0] == g.nc[1] and 355 <= g.nc[0] <= 370
     assert 3 <= g.nc[2] <= 32
     assert g.ncode <= 8 * (1 << 20)
+
+
+def test_grid_plan_widens_sparse_cells(lib):
+    """Fewer than ~5 particles per narrowest cell: cells grow towards 8 per cell (never below the list
+    radius); denser grids keep the narrowest cells."""
+    n = 161 ** 3
+    rc, g = _plan(lib, (161., 161., 161.), 1.5, 0.0, n)               # 3.4 per cell of width 1.5
+    assert rc == 0 and g.nc[0] == g.nc[1] == g.nc[2]
+    assert 7.0 <= n / g.nc[0] ** 3 <= 9.5 and g.w[0] >= 1.5
+    rc, g = _plan(lib, (161 * 1.26,) * 3, 2.0, 0.0, n)                # density 0.5: 4 per cell of width 2
+    assert rc == 0 and 7.0 <= n / (g.nc[0] * g.nc[1] * g.nc[2]) <= 9.5
+    rc, g = _plan(lib, (256., 256., 256.), 2.0, 0.0, 1 << 24)         # 8 per cell already
+    assert rc == 0 and g.nc[0] == g.nc[1] == g.nc[2] == 127
+    rc, g = _plan(lib, (256., 256., 256.), 2.0, 0.0, 0)               # no particle count: narrowest cells
+    assert rc == 0 and g.nc[0] == 127
+    rc, g = _plan(lib, (20., 20., 20.), 2.0, 0.0, 400)                # tiny and sparse: never fewer than 3 layers
+    assert rc == 0 and min(g.nc[0], g.nc[1], g.nc[2]) >= 3
 
 
 def test_grid_plan_rejects_bad_input(lib):

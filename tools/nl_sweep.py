@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--max-n", type=int, default=1 << 26)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--reference", action="store_true")
+    ap.add_argument("--logn", type=int, nargs="*", default=[20, 22, 24, 26, 28], help="log2 of the particle counts")
     a = ap.parse_args()
     if a.reference:
         return reference_sweep()
@@ -54,7 +55,7 @@ def main():
     dev = torch.device("cuda", 0)
     print("# N, density, cutoff, pairs/particle, ms per build, particles/s, pairs/s, alg GB/s, frac of %.0f GB/s, "
           "neighbour kernel (tile = cell-group kernel, general = warp-per-cell kernel after SPH_F_TILE_FALLBACK)" % peak)
-    for logn in (20, 22, 24, 26, 28):
+    for logn in a.logn:
         n_target = 1 << logn
         if n_target > a.max_n:
             break
