@@ -76,6 +76,15 @@
 #ifndef SPH_ROW_PIPE
 #define SPH_ROW_PIPE 0
 #endif
+//   SPH_FORCE_PAIRLOAD  1 (needs SPH_ROW_STRIDE=8): lanes 2i, 2i+1 of the force pass fetch each neighbour's 64-byte row
+//                    together, half a row per lane in ONE request (16 lines per request instead of 32), and pass each
+//                    other the half they lack by shuffle
+#ifndef SPH_FORCE_PAIRLOAD
+#define SPH_FORCE_PAIRLOAD 0
+#endif
+#if SPH_FORCE_PAIRLOAD && SPH_ROW_STRIDE != 8
+#error "SPH_FORCE_PAIRLOAD needs the interleaved rows of SPH_ROW_STRIDE=8"
+#endif
 #ifndef SPH_PP_SMQ
 #define SPH_PP_SMQ 0
 #endif
@@ -313,8 +322,8 @@ gather_kernel(const __grid_constant__ sph_grid g, int n, const int32_t *__restri
     const size_t i = (size_t)perm[a];
     const double x = r[3 * i], y = r[3 * i + 1], z = r[3 * i + 2];
     const CellLoc c = locate(g, x, y, z);
-    store4(pos4 + 4 * (size_t)a, x, y, z, m[i]);
-    store4(vel4 + 4 * (size_t)a, v[3 * i], v[3 * i + 1], v[3 * i + 2], 0.0);
+    store4(pos4 + kRowD * (size_t)a, x, y, z, m[i]);
+    store4(vel4 + kRowD * (size_t)a, v[3 * i], v[3 * i + 1], v[3 * i + 2], 0.0);
     reinterpret_cast<float4 *>(rel4)[a] = make_float4(c.rx, c.ry, c.rz, __uint_as_float(c.interior ? 1u : 0u));
 }
 
@@ -581,7 +590,7 @@ __device__ __forceinline__ double density_row(const sph_grid &g, const double *_
 #pragma unroll
         for (int u = 0; u < kRowU; ++u) {
             j[u] = jn[0][u];
-            load_row4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
+            load_row4(pos4 + kRowD * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
         }
 #pragma unroll
         for (int u = 0; u < kRowU; ++u) {
@@ -639,7 +648,7 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
     int count = 0, orig = 0;
     bool interior = true;
     if (active) {
-        load4(pos4 + 4 * (size_t)a, ax, ay, az, am);
+        load4(pos4 + kRowD * (size_t)a, ax, ay, az, am);
         count = min(cnt[a], K);
         orig = perm[a];
         interior = cell_is_interior(g, __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w));
@@ -668,7 +677,7 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
     pco_out[orig] = pco;
     u_out[orig] = u;
     t_io[orig] = (u + eos.adash * rho) / eos.kbdash;                        // properties.py:49,120
-    vel4[4 * (size_t)a + 3] = p / (rho * rho);                              // forces.py:353 operand
+    vel4[kRowD * (size_t)a + 3] = p / (rho * rho);                              // forces.py:353 operand
     });
 }
 
@@ -681,7 +690,7 @@ pressure_term_kernel(int n, int first_orig, const int32_t *__restrict__ perm, co
     const int o = perm[a];
     if (o < first_orig) return;
     const double d = rho[o];
-    vel4[4 * (size_t)a + 3] = press[o] / (d * d);
+    vel4[kRowD * (size_t)a + 3] = press[o] / (d * d);
 }
 
 struct ForceAcc { double ax, ay, az, du; };
@@ -715,8 +724,8 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
             jn[st][u] = (st + 1) * kRowUF + u < count ? load_idx(row + (size_t)((st + 1) * kRowUF + u) * stride) : self;
 #pragma unroll
     for (int u = 0; u < kRowUF; ++u) {
-        load_row4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
-        load_row4(vel4 + 4 * (size_t)j[u], wx[u], wy[u], wz[u], Aj[u]);
+        load_row4(pos4 + kRowD * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
+        load_row4(vel4 + kRowD * (size_t)j[u], wx[u], wy[u], wz[u], Aj[u]);
     }
     for (int k0 = 0; k0 < count; k0 += kRowUF) {
         double nbx[kRowUF], nby[kRowUF], nbz[kRowUF], nbm[kRowUF], nwx[kRowUF], nwy[kRowUF], nwz[kRowUF], nAj[kRowUF];
@@ -724,8 +733,8 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
             nj[u] = jn[0][u];
-            load_row4(pos4 + 4 * (size_t)nj[u], nbx[u], nby[u], nbz[u], nbm[u]);
-            load_row4(vel4 + 4 * (size_t)nj[u], nwx[u], nwy[u], nwz[u], nAj[u]);
+            load_row4(pos4 + kRowD * (size_t)nj[u], nbx[u], nby[u], nbz[u], nbm[u]);
+            load_row4(vel4 + kRowD * (size_t)nj[u], nwx[u], nwy[u], nwz[u], nAj[u]);
         }
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
@@ -747,8 +756,8 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
             j[u] = jn[0][u];
-            load_row4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
-            load_row4(vel4 + 4 * (size_t)j[u], wx[u], wy[u], wz[u], Aj[u]);
+            load_row4(pos4 + kRowD * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
+            load_row4(vel4 + kRowD * (size_t)j[u], wx[u], wy[u], wz[u], Aj[u]);
         }
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
@@ -804,6 +813,78 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
     return f;
 }
 
+#if SPH_FORCE_PAIRLOAD
+// Force row with lane-pair gathers (one lane per particle as before).  L1 retires one wavefront per 128-byte line
+// a request touches; a lane loading the two 32-byte halves of its neighbour's state costs two lines.  Here the lanes
+// 2i and 2i+1 read, in one request, the position half (even lane) and the velocity half (odd lane) of the SAME
+// 64-byte row: first the even lane's neighbour, then the odd lane's.  Each lane then holds one half of its own
+// neighbour and one half of its partner's, and a shuffle swaps the foreign halves.  Every lane runs the warp's
+// longest row (the shuffles need all lanes); trips past a lane's own count gather its own row and add nothing.
+// The arithmetic is that of force_row, term by term.
+template <bool UNIFORM_H, bool WRAP>
+__device__ __forceinline__ ForceAcc force_row_pair(const sph_grid &g, const double *__restrict__ rows8,
+                                                   const int32_t *__restrict__ perm,
+                                                   const double *__restrict__ h_orig,
+                                                   const int32_t *__restrict__ row, int count, int orig, int self,
+                                                   double px, double py, double pz, double vx, double vy, double vz,
+                                                   double Ai, double hinv, double c2, double fcutsq, bool two_d)
+{
+    ForceAcc f = {0.0, 0.0, 0.0, 0.0};
+    const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
+    const unsigned full = 0xffffffffu;
+    const bool odd = (threadIdx.x & 1) != 0;
+    const size_t half = odd ? 4 : 0;
+    const int trips = __reduce_max_sync(full, count);
+    int jn0 = 0 < count ? load_idx(row) : self;
+    int jn1 = 1 < count ? load_idx(row + 32) : self;
+    for (int k = 0; k < trips; ++k) {
+        const int jme = jn0;
+        jn0 = jn1;
+        jn1 = k + 2 < count ? load_idx(row + (size_t)(k + 2) * 32) : self;
+        const int jpartner = __shfl_xor_sync(full, jme, 1);
+        const int je = odd ? jpartner : jme;          // neighbour of the pair's even lane
+        const int jo = odd ? jme : jpartner;          // neighbour of the pair's odd lane
+        double a0, a1, a2, a3, b0, b1, b2, b3;
+        load_row4(rows8 + 8 * (size_t)je + half, a0, a1, a2, a3);     // even lane: position of je, odd lane: velocity of je
+        load_row4(rows8 + 8 * (size_t)jo + half, b0, b1, b2, b3);     // even lane: position of jo, odd lane: velocity of jo
+        // the even lane lacks the velocity of je (the odd lane's a), the odd lane the position of jo (the even lane's b)
+        const double r0 = __shfl_xor_sync(full, odd ? a0 : b0, 1);
+        const double r1 = __shfl_xor_sync(full, odd ? a1 : b1, 1);
+        const double r2 = __shfl_xor_sync(full, odd ? a2 : b2, 1);
+        const double r3 = __shfl_xor_sync(full, odd ? a3 : b3, 1);
+        const double bx = odd ? r0 : a0, by = odd ? r1 : a1, bz = odd ? r2 : a2, bm = odd ? r3 : a3;
+        const double wx = odd ? b0 : r0, wy = odd ? b1 : r1, wz = odd ? b2 : r2, Aj = odd ? b3 : r3;
+        double dx = bx - px, dy = by - py, dz = bz - pz;
+        if (WRAP) {
+            dx = min_image(dx, g.box[0], hx);
+            dy = min_image(dy, g.box[1], hy);
+            dz = min_image(dz, g.box[2], hz);
+        }
+        const double rsq = rsq_exact(dx, dy, dz);
+        const double rr = sqrt(rsq);
+        double hi = hinv, cc = c2;
+        if (!UNIFORM_H) {
+            const int oj = perm[jme];
+            const double h = h_orig[oj < orig ? oj : orig];
+            hi = 1.0 / h;
+            cc = -12.0 * lucy_norm3(h) * hi * hi;
+        }
+        const double s = rr * hi;
+        if (s < 1.0 && rr * rr <= fcutsq && k < count) {
+            const double t = 1.0 - s;
+            const double fac = (cc * (t * t)) * (Ai + Aj);
+            const double gx = fac * dx, gy = fac * dy, gz = two_d ? 0.0 : fac * dz;
+            f.ax += gx;
+            f.ay += gy;
+            f.az += gz;
+            const double dot = gx * (wx - vx) + gy * (wy - vy) + gz * (wz - vz);
+            f.du += (0.5 * dot) * bm;
+        }
+    }
+    return f;
+}
+#endif
+
 template <bool UNIFORM_H, int LPP>
 __global__ void __launch_bounds__(kPPBlock, SPH_FORCE_MINB)
 force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__restrict__ pos4,
@@ -821,8 +902,8 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
     int count = 0, orig = 0;
     bool interior = true;
     if (active) {
-        load4(pos4 + 4 * (size_t)a, px, py, pz, pm);
-        load4(vel4 + 4 * (size_t)a, vx, vy, vz, Ai);
+        load4(pos4 + kRowD * (size_t)a, px, py, pz, pm);
+        load4(vel4 + kRowD * (size_t)a, vx, vy, vz, Ai);
         count = min(cnt[a], K);
         orig = perm[a];
         interior = cell_is_interior(g, __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w));
@@ -834,6 +915,14 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
     const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K + q) * 32 + (a & 31);
     const int mine = count > q ? (count - q + LPP - 1) / LPP : 0;
     ForceAcc f;
+#if SPH_FORCE_PAIRLOAD
+    if (LPP == 1) {
+        const int self = active ? a : 0;                // lanes past the end still gather (a valid row) with the others
+        const int32_t *rowp = active ? row : nbr;
+        if (skip) f = force_row_pair<UNIFORM_H, false>(g, pos4, perm, h_orig, rowp, count, orig, self, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
+        else f = force_row_pair<UNIFORM_H, true>(g, pos4, perm, h_orig, rowp, count, orig, self, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
+    } else
+#endif
     if (skip) f = force_row<UNIFORM_H, false>(g, pos4, vel4, perm, h_orig, row, (size_t)32 * LPP, mine, orig, a, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
     else f = force_row<UNIFORM_H, true>(g, pos4, vel4, perm, h_orig, row, (size_t)32 * LPP, mine, orig, a, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
 #pragma unroll
@@ -885,7 +974,7 @@ __device__ __forceinline__ double conduction_row(const sph_grid &g, const double
 #pragma unroll
         for (int u = 0; u < kRowUC; ++u) {
             j[u] = jn[u];
-            load4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
+            load4(pos4 + kRowD * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
             load4(aux4 + 4 * (size_t)j[u], ex[u], ey[u], ez[u], ew[u]);
         }
 #pragma unroll
@@ -935,7 +1024,7 @@ conduction_kernel(const __grid_constant__ sph_grid g, int n, int K, const double
     int count = 0, orig = 0;
     bool interior = true;
     if (active) {
-        load4(pos4 + 4 * (size_t)a, px, py, pz, pm);
+        load4(pos4 + kRowD * (size_t)a, px, py, pz, pm);
         load4(aux4 + 4 * (size_t)a, qx, qy, qz, qw);
         count = min(cnt[a], K);
         orig = perm[a];
@@ -1340,6 +1429,8 @@ int64_t sph_scan_tmp_elems(uint32_t ncode)
     return ((int64_t)ncode + kScanTile - 1) / kScanTile + 2 + kQueueSlots;
 }
 
+int sph_row_doubles(void) { return kRowD; }
+
 int64_t sph_nbr_elems(int32_t n, int32_t max_nbrs)
 {
     return (((int64_t)n + 31) / 32) * 32 * (int64_t)max_nbrs;
@@ -1544,6 +1635,7 @@ int sph_gather(const sph_grid *g, const sph_buffers *b, const double *d_r, const
                const double *d_m, void *stream)
 {
     if (!g || !b || !d_r || !d_v || !d_m || !b->pos4 || !b->vel4 || !b->rel4 || !b->perm) return SPH_E_BADARG;
+    if (kRowD == 8 && b->vel4 != b->pos4 + 4) return SPH_E_BADARG;      // interleaved rows: see sph_row_doubles()
     if (b->n > 0)
         gather_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
             *g, b->n, b->perm, d_r, d_v, d_m, b->pos4, b->vel4, b->rel4);

@@ -57,6 +57,9 @@ VARIANTS = {
     "w_f_pipe_r80": _v(W, SPH_FORCE_MINB=6, SPH_ROW_PIPE=1),
     "w_f_r64": _v(W, SPH_FORCE_MINB=8),
     "base_smq": _v(R1E, SPH_PP_SMQ=1),
+    # interleaved 64-byte rows and lane-pair gathers in the force pass
+    "w_stride8": _v(W, SPH_ROW_STRIDE=8),
+    "w_pairload": _v(W, SPH_ROW_STRIDE=8, SPH_FORCE_PAIRLOAD=1),
 }
 
 
