@@ -37,7 +37,7 @@ def launches(path):
         v = float(r[vi].replace(",", ""))
         v = v / 1e3 if r[ui] == "ns" else (v * 1e3 if r[ui] == "ms" else v)
         agg.setdefault(r[ki].split("(")[0], []).append(v)
-    ours = {k: v for k, v in agg.items() if "<unnamed>::" in k}
+    ours = {k: v for k, v in agg.items() if k.startswith(("<unnamed>::", "void <unnamed>::"))}   # torch's have at:: in front
     per_eval = sum(sum(v) / len(v) for v in ours.values())
     print("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised): compare SHARES")
     print("%-58s %6s %12s %8s" % ("kernel", "n", "mean us", "share"))
