@@ -85,6 +85,13 @@
 #if SPH_FORCE_PAIRLOAD && SPH_ROW_STRIDE != 8
 #error "SPH_FORCE_PAIRLOAD needs the interleaved rows of SPH_ROW_STRIDE=8"
 #endif
+//   SPH_INTRA_SHFL   1: neighbours that sit in the same warp (consecutive sorted particles: ~36 % of the directed
+//                    pairs on the bench lattice) are taken from the other lane's registers by shuffle instead of
+//                    being gathered through L1; only lanes whose neighbour is outside the warp issue a load.  Best with
+//                    rows that list the in-warp neighbours first (SPH_SORT_ROWS=2, a diagnostic partition pass)
+#ifndef SPH_INTRA_SHFL
+#define SPH_INTRA_SHFL 0
+#endif
 #ifndef SPH_PP_SMQ
 #define SPH_PP_SMQ 0
 #endif
@@ -626,6 +633,63 @@ __device__ __forceinline__ double density_row(const sph_grid &g, const double *_
     return acc;
 }
 
+#if SPH_INTRA_SHFL
+// Density row, one neighbour per trip; every lane runs the warp's longest row because the shuffles need all lanes.
+// A neighbour j with j >> 5 == self >> 5 is the particle of lane j & 31 of this warp: its row (x y z m) is in that
+// lane's registers.  Other neighbours are gathered as in density_row, by the lanes that need them only.
+template <bool UNIFORM_H, bool WRAP>
+__device__ __forceinline__ double density_row_shfl(const sph_grid &g, const double *__restrict__ pos4,
+                                                   const int32_t *__restrict__ perm,
+                                                   const double *__restrict__ h_orig,
+                                                   const int32_t *__restrict__ row, int count, int orig, int self,
+                                                   double ax, double ay, double az, double am, double hinv, double qn)
+{
+    double acc = 0.0;
+    const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
+    const unsigned full = 0xffffffffu;
+    const int wid = self >> 5;
+    const int trips = __reduce_max_sync(full, count);
+    int jn0 = 0 < count ? load_idx(row) : self;
+    int jn1 = 1 < count ? load_idx(row + 32) : self;
+    for (int k = 0; k < trips; ++k) {
+        const int j = jn0;
+        jn0 = jn1;
+        jn1 = k + 2 < count ? load_idx(row + (size_t)(k + 2) * 32) : self;
+        const bool valid = k < count;
+        const bool intra = valid && (j >> 5) == wid;
+        double bx = ax, by = ay, bz = az, bm = 0.0;
+        if (valid && !intra) load_row4(pos4 + kRowD * (size_t)j, bx, by, bz, bm);
+        if (__any_sync(full, intra)) {
+            const int src = j & 31;
+            const double sx = __shfl_sync(full, ax, src), sy = __shfl_sync(full, ay, src);
+            const double sz = __shfl_sync(full, az, src), sm = __shfl_sync(full, am, src);
+            if (intra) { bx = sx; by = sy; bz = sz; bm = sm; }
+        }
+        double dx = bx - ax, dy = by - ay, dz = bz - az;
+        if (WRAP) {
+            dx = min_image(dx, g.box[0], hx);
+            dy = min_image(dy, g.box[1], hy);
+            dz = min_image(dz, g.box[2], hz);
+        }
+        const double rsq = rsq_exact(dx, dy, dz);
+        const double rr = sqrt(rsq);
+        double hi = hinv, q = qn;
+        if (!UNIFORM_H) {
+            const int oj = perm[j];
+            const double h = h_orig[oj < orig ? oj : orig];
+            hi = 1.0 / h;
+            q = lucy_norm3(h);
+        }
+        const double s = rr * hi;
+        if (s < 1.0 && valid) {
+            const double t = 1.0 - s;
+            acc += (q * (1.0 + 3.0 * s) * (t * t * t)) * bm;
+        }
+    }
+    return acc;
+}
+#endif
+
 // LPP lanes cooperate on one particle: lane q of the group takes neighbours q, q+LPP, ... of the
 // row, so that the lanes of a group gather consecutive rows (neighbours from one cell are
 // contiguous in the sorted arrays) and the per-lane trip counts even out; the partial sums are
@@ -660,6 +724,14 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
     const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K + q) * 32 + (a & 31);
     const int mine = count > q ? (count - q + LPP - 1) / LPP : 0;
     double sum;
+#if SPH_INTRA_SHFL
+    if (LPP == 1) {
+        const int self = active ? a : 0;
+        const int32_t *rowp = active ? row : nbr;
+        if (skip) sum = density_row_shfl<UNIFORM_H, false>(g, pos4, perm, h_orig, rowp, count, orig, self, ax, ay, az, am, hinv, qn);
+        else sum = density_row_shfl<UNIFORM_H, true>(g, pos4, perm, h_orig, rowp, count, orig, self, ax, ay, az, am, hinv, qn);
+    } else
+#endif
     if (skip) sum = density_row<UNIFORM_H, false>(g, pos4, perm, h_orig, row, (size_t)32 * LPP, mine, orig, a, ax, ay, az, hinv, qn);
     else sum = density_row<UNIFORM_H, true>(g, pos4, perm, h_orig, row, (size_t)32 * LPP, mine, orig, a, ax, ay, az, hinv, qn);
 #pragma unroll
@@ -813,6 +885,76 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
     return f;
 }
 
+#if SPH_INTRA_SHFL
+// Force row with in-warp neighbours taken by shuffle (see density_row_shfl): eight doubles per neighbour come from
+// the registers of lane j & 31 when j is a particle of this warp, from two gathered rows otherwise.
+template <bool UNIFORM_H, bool WRAP>
+__device__ __forceinline__ ForceAcc force_row_shfl(const sph_grid &g, const double *__restrict__ pos4,
+                                                   const double *__restrict__ vel4,
+                                                   const int32_t *__restrict__ perm,
+                                                   const double *__restrict__ h_orig,
+                                                   const int32_t *__restrict__ row, int count, int orig, int self,
+                                                   double px, double py, double pz, double pm, double vx, double vy,
+                                                   double vz, double Ai, double hinv, double c2, double fcutsq,
+                                                   bool two_d)
+{
+    ForceAcc f = {0.0, 0.0, 0.0, 0.0};
+    const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
+    const unsigned full = 0xffffffffu;
+    const int wid = self >> 5;
+    const int trips = __reduce_max_sync(full, count);
+    int jn0 = 0 < count ? load_idx(row) : self;
+    int jn1 = 1 < count ? load_idx(row + 32) : self;
+    for (int k = 0; k < trips; ++k) {
+        const int j = jn0;
+        jn0 = jn1;
+        jn1 = k + 2 < count ? load_idx(row + (size_t)(k + 2) * 32) : self;
+        const bool valid = k < count;
+        const bool intra = valid && (j >> 5) == wid;
+        double bx = px, by = py, bz = pz, bm = 0.0, wx = vx, wy = vy, wz = vz, Aj = Ai;
+        if (valid && !intra) {
+            load_row4(pos4 + kRowD * (size_t)j, bx, by, bz, bm);
+            load_row4(vel4 + kRowD * (size_t)j, wx, wy, wz, Aj);
+        }
+        if (__any_sync(full, intra)) {
+            const int src = j & 31;
+            const double s0 = __shfl_sync(full, px, src), s1 = __shfl_sync(full, py, src);
+            const double s2 = __shfl_sync(full, pz, src), s3 = __shfl_sync(full, pm, src);
+            const double s4 = __shfl_sync(full, vx, src), s5 = __shfl_sync(full, vy, src);
+            const double s6 = __shfl_sync(full, vz, src), s7 = __shfl_sync(full, Ai, src);
+            if (intra) { bx = s0; by = s1; bz = s2; bm = s3; wx = s4; wy = s5; wz = s6; Aj = s7; }
+        }
+        double dx = bx - px, dy = by - py, dz = bz - pz;
+        if (WRAP) {
+            dx = min_image(dx, g.box[0], hx);
+            dy = min_image(dy, g.box[1], hy);
+            dz = min_image(dz, g.box[2], hz);
+        }
+        const double rsq = rsq_exact(dx, dy, dz);
+        const double rr = sqrt(rsq);
+        double hi = hinv, cc = c2;
+        if (!UNIFORM_H) {
+            const int oj = perm[j];
+            const double h = h_orig[oj < orig ? oj : orig];
+            hi = 1.0 / h;
+            cc = -12.0 * lucy_norm3(h) * hi * hi;
+        }
+        const double s = rr * hi;
+        if (s < 1.0 && rr * rr <= fcutsq && valid) {
+            const double t = 1.0 - s;
+            const double fac = (cc * (t * t)) * (Ai + Aj);
+            const double gx = fac * dx, gy = fac * dy, gz = two_d ? 0.0 : fac * dz;
+            f.ax += gx;
+            f.ay += gy;
+            f.az += gz;
+            const double dot = gx * (wx - vx) + gy * (wy - vy) + gz * (wz - vz);
+            f.du += (0.5 * dot) * bm;
+        }
+    }
+    return f;
+}
+#endif
+
 #if SPH_FORCE_PAIRLOAD
 // Force row with lane-pair gathers (one lane per particle as before).  L1 retires one wavefront per 128-byte line
 // a request touches; a lane loading the two 32-byte halves of its neighbour's state costs two lines.  Here the lanes
@@ -915,7 +1057,14 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
     const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K + q) * 32 + (a & 31);
     const int mine = count > q ? (count - q + LPP - 1) / LPP : 0;
     ForceAcc f;
-#if SPH_FORCE_PAIRLOAD
+#if SPH_INTRA_SHFL
+    if (LPP == 1) {
+        const int self = active ? a : 0;
+        const int32_t *rowp = active ? row : nbr;
+        if (skip) f = force_row_shfl<UNIFORM_H, false>(g, pos4, vel4, perm, h_orig, rowp, count, orig, self, px, py, pz, pm, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
+        else f = force_row_shfl<UNIFORM_H, true>(g, pos4, vel4, perm, h_orig, rowp, count, orig, self, px, py, pz, pm, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
+    } else
+#elif SPH_FORCE_PAIRLOAD
     if (LPP == 1) {
         const int self = active ? a : 0;                // lanes past the end still gather (a valid row) with the others
         const int32_t *rowp = active ? row : nbr;
@@ -1324,11 +1473,12 @@ inline int launch_status()
     return e == cudaSuccess ? SPH_OK : (int)e;
 }
 
-// Diagnostic (SPH_SORT_ROWS=1 in the environment): rewrite every ELL row in ascending order of the sorted
-// neighbour index after the neighbour pass, to measure what a common sweep order of the lanes of a warp is
-// worth to the gathers of the density / force passes.  Not tuned: one thread per row, local-memory sort.
+// Diagnostic (SPH_SORT_ROWS in the environment), run after the neighbour pass.  1: rewrite every ELL row in ascending
+// order of the sorted neighbour index, to measure what a common sweep order of the lanes of a warp is worth to the
+// gathers of the density / force passes.  2: stable partition, the neighbours inside the particle's own warp first
+// (for builds with SPH_INTRA_SHFL).  Not tuned: one thread per row, local-memory copy.
 __global__ void __launch_bounds__(kBlock)
-row_sort_kernel(int n, int K, int32_t *__restrict__ nbr, const int32_t *__restrict__ cnt)
+row_sort_kernel(int n, int K, int32_t *__restrict__ nbr, const int32_t *__restrict__ cnt, int mode)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
@@ -1338,6 +1488,14 @@ row_sort_kernel(int n, int K, int32_t *__restrict__ nbr, const int32_t *__restri
     int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
     int32_t v[kMax];
     for (int k = 0; k < c; ++k) v[k] = row[(size_t)k * 32];
+    if (mode == 2) {                        // stable partition: neighbours inside this particle's warp first
+        int w = 0;
+        for (int k = 0; k < c; ++k)
+            if ((v[k] >> 5) == (a >> 5)) row[(size_t)(w++) * 32] = v[k];
+        for (int k = 0; k < c; ++k)
+            if ((v[k] >> 5) != (a >> 5)) row[(size_t)(w++) * 32] = v[k];
+        return;
+    }
     for (int i = 1; i < c; ++i) {
         const int32_t x = v[i];
         int j = i - 1;
@@ -1685,7 +1843,7 @@ int sph_nlist_build(const sph_grid *g, const sph_buffers *b, void *stream)
         sort_rows = e ? atoi(e) : 0;
     }
     if (rc == SPH_OK && sort_rows)
-        row_sort_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, s>>>(b->n, b->max_nbrs, b->nbr, b->cnt);
+        row_sort_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, s>>>(b->n, b->max_nbrs, b->nbr, b->cnt, sort_rows);
     return rc;
 }
 

@@ -60,6 +60,10 @@ VARIANTS = {
     # interleaved 64-byte rows and lane-pair gathers in the force pass
     "w_stride8": _v(W, SPH_ROW_STRIDE=8),
     "w_pairload": _v(W, SPH_ROW_STRIDE=8, SPH_FORCE_PAIRLOAD=1),
+    # in-warp neighbours by shuffle (run with SPH_SORT_ROWS=2 in the environment to list them first; the sums then run
+    # in another order, so the digest differs from the default build in the last bits)
+    "w_intra": _v(W, SPH_INTRA_SHFL=1),
+    "w_intra_d8": _v(W, SPH_INTRA_SHFL=1, SPH_DENS_MINB=8),
 }
 
 
