@@ -131,10 +131,6 @@ int sph_grid_restrict_x(sph_grid *grid, int32_t first_layer, int32_t n_layers);
 
 /* Elements needed in sph_buffers.scan_tmp for a grid with `ncode` cell codes. */
 int64_t sph_scan_tmp_elems(uint32_t ncode);
-/* Doubles per row of the Morton-sorted state this build of the library works on.  4 (the default): pos4 and
- * vel4 are two separate [n,4] arrays.  8: ONE [n,8] array of interleaved 64-byte rows (x y z m vx vy vz
- * press/rho^2) with sph_buffers.vel4 == sph_buffers.pos4 + 4; sph_gather returns SPH_E_BADARG otherwise. */
-int sph_row_doubles(void);
 /* Elements needed in sph_buffers.nbr. */
 int64_t sph_nbr_elems(int32_t n, int32_t max_nbrs);
 

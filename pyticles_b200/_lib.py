@@ -92,7 +92,6 @@ SIGNATURES = {
     "sph_grid_plan": (ctypes.c_int, [_d3, _dbl, _dbl, _i64, _d3, _d3, _gp]),
     "sph_grid_restrict_x": (ctypes.c_int, [_gp, _i32, _i32]),
     "sph_scan_tmp_elems": (_i64, [ctypes.c_uint32]),
-    "sph_row_doubles": (ctypes.c_int, []),
     "sph_nbr_elems": (_i64, [_i32, _i32]),
     "sph_status_reset": (ctypes.c_int, [_vp, _vp]),
     "sph_cells_build": (ctypes.c_int, [_gp, _bp, _vp, _vp]),

@@ -102,13 +102,8 @@ class NeighbourBackend(object):
         b.code = _ptr(self._alloc("code", n, torch.int32))
         b.rank = _ptr(self._alloc("rank", n, torch.int32))
         b.perm = _ptr(self._alloc("perm", n, torch.int32))
-        if self.lib.sph_row_doubles() == 8:          # a build with interleaved 64-byte rows: vel4 = pos4 + 4 doubles
-            rows = self._alloc("rows8", 8 * n, torch.float64)
-            b.pos4 = ctypes.c_void_p(rows.data_ptr())
-            b.vel4 = ctypes.c_void_p(rows.data_ptr() + 32)
-        else:
-            b.pos4 = _ptr(self._alloc("pos4", 4 * n, torch.float64))
-            b.vel4 = _ptr(self._alloc("vel4", 4 * n, torch.float64))
+        b.pos4 = _ptr(self._alloc("pos4", 4 * n, torch.float64))
+        b.vel4 = _ptr(self._alloc("vel4", 4 * n, torch.float64))
         b.rel4 = _ptr(self._alloc("rel4", 4 * n, torch.float32))
         b.nbr = _ptr(self._alloc("nbr", self.lib.sph_nbr_elems(n, self.K), torch.int32))
         b.cnt = _ptr(self._alloc("cnt", n, torch.int32))

@@ -13,15 +13,6 @@
 
 namespace {
 
-// Doubles per row of the Morton-sorted particle state.  4: pos4 (x y z m) and vel4 (vx vy vz press/rho^2) are two
-// [n,4] arrays.  8: one [n,8] array of interleaved 64-byte rows, sph_buffers.vel4 == sph_buffers.pos4 + 4 -- the
-// layout the lane-pair gathers of the force pass need (SPH_FORCE_PAIRLOAD).  sph_row_doubles() reports it.
-#ifndef SPH_ROW_STRIDE
-#define SPH_ROW_STRIDE 4
-#endif
-constexpr int kRowD = SPH_ROW_STRIDE;
-static_assert(kRowD == 4 || kRowD == 8, "SPH_ROW_STRIDE is 4 or 8");
-
 constexpr int kBlock = 256;
 constexpr int kNlWarps = 8;          // warps per block in the neighbour pass
 constexpr int kNlWin = 512;          // candidates staged per warp per window
@@ -83,8 +74,8 @@ __device__ __forceinline__ double rsq_exact(double dx, double dy, double dz)
 __device__ __forceinline__ bool pair_exact(const sph_grid &g, const double *pos4, int a, int j)
 {
     double ax, ay, az, am, bx, by, bz, bm;
-    load4(pos4 + kRowD * (size_t)a, ax, ay, az, am);
-    load4(pos4 + kRowD * (size_t)j, bx, by, bz, bm);
+    load4(pos4 + 4 * (size_t)a, ax, ay, az, am);
+    load4(pos4 + 4 * (size_t)j, bx, by, bz, bm);
     const double dx = min_image(__dsub_rn(bx, ax), g.box[0], g.box[0] / 2.);
     const double dy = min_image(__dsub_rn(by, ay), g.box[1], g.box[1] / 2.);
     const double dz = min_image(__dsub_rn(bz, az), g.box[2], g.box[2] / 2.);

@@ -38,14 +38,8 @@
 //   SPH_PP_BLOCK     threads per block            SPH_DENS_MINB / SPH_FORCE_MINB   __launch_bounds__ min blocks
 //   SPH_ROW_U / SPH_ROW_UF   neighbours gathered per pipeline stage (density / force)
 //   SPH_IDX_AHEAD / SPH_IDX_AHEAD_F   pipeline stages the neighbour indices are fetched ahead of their rows
-//   SPH_IDX_NOALLOC  1: neighbour-index loads bypass L1 allocation      (measured: no effect)
-//   SPH_ROW_KEEP     1: gathered rows are loaded with L1::evict_last    (measured: no effect)
-//   SPH_ROW_PIPE     1: force pass requests the rows of the next stage before it evaluates the current one
-//                    (measured: slower, the second row buffer spills under the register cap)
-//   SPH_PP_SMQ       1: persistent blocks take chunks of kPPBlock particles from per-SM queues (%smid), so that the
-//                    blocks resident on one SM work on adjacent stretches of the Morton order and share gathered
-//                    rows in that SM's L1; an SM whose queue is empty steals from the others (measured: 3 % slower)
-//   SPH_PP_MAXL1     1: ask for the largest L1 (shared-memory carve-out 0)    (measured: no effect)
+// Other variants of these passes were built, measured and taken out again (cache hints, double-buffered rows,
+// per-SM chunk queues, lane-pair gathers of interleaved rows, in-warp neighbours by shuffle): DESIGN.md section 5.
 #ifndef SPH_PP_BLOCK
 #define SPH_PP_BLOCK 128
 #endif
@@ -67,128 +61,10 @@
 #ifndef SPH_IDX_AHEAD_F
 #define SPH_IDX_AHEAD_F SPH_IDX_AHEAD
 #endif
-#ifndef SPH_IDX_NOALLOC
-#define SPH_IDX_NOALLOC 0
-#endif
-#ifndef SPH_ROW_KEEP
-#define SPH_ROW_KEEP 0
-#endif
-#ifndef SPH_ROW_PIPE
-#define SPH_ROW_PIPE 0
-#endif
-//   SPH_FORCE_PAIRLOAD  1 (needs SPH_ROW_STRIDE=8): lanes 2i, 2i+1 of the force pass fetch each neighbour's 64-byte row
-//                    together, half a row per lane in ONE request (16 lines per request instead of 32), and pass each
-//                    other the half they lack by shuffle
-#ifndef SPH_FORCE_PAIRLOAD
-#define SPH_FORCE_PAIRLOAD 0
-#endif
-#if SPH_FORCE_PAIRLOAD && SPH_ROW_STRIDE != 8
-#error "SPH_FORCE_PAIRLOAD needs the interleaved rows of SPH_ROW_STRIDE=8"
-#endif
-//   SPH_INTRA_SHFL   1: neighbours that sit in the same warp (consecutive sorted particles: ~36 % of the directed
-//                    pairs on the bench lattice) are taken from the other lane's registers by shuffle instead of
-//                    being gathered through L1; only lanes whose neighbour is outside the warp issue a load.  Best with
-//                    rows that list the in-warp neighbours first (SPH_SORT_ROWS=2, a diagnostic partition pass)
-#ifndef SPH_INTRA_SHFL
-#define SPH_INTRA_SHFL 0
-#endif
-#ifndef SPH_PP_SMQ
-#define SPH_PP_SMQ 0
-#endif
-#ifndef SPH_PP_MAXL1
-#define SPH_PP_MAXL1 0
-#endif
 
 namespace {
 
 constexpr int kPPBlock = SPH_PP_BLOCK;
-
-__device__ __forceinline__ void load_row4(const double *p, double &a, double &b, double &c, double &d)
-{
-#if SPH_ROW_KEEP
-    asm volatile("ld.global.nc.L1::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
-#else
-    load4(p, a, b, c, d);
-#endif
-}
-
-// Work distribution of the per-particle passes.  queue == nullptr: block b does chunk b.  Otherwise the grid
-// is persistent and chunk c belongs to queue c / per_queue; a block starts on the queue of the SM it runs on
-// and moves on to the next queue when one is drained, so every chunk is done exactly once wherever the blocks
-// land.  queue[] is zeroed before the launch.
-struct ChunkQueue {
-    uint32_t *queue;
-    int nq, per_queue, nchunks;
-};
-
-#if SPH_PP_SMQ
-__device__ __forceinline__ uint32_t sm_id()
-{
-    uint32_t v;
-    asm("mov.u32 %0, %%smid;" : "=r"(v));
-    return v;
-}
-
-// thread 0 only; the probe position lives in shared memory so that it costs no register in the pass itself
-__device__ __forceinline__ int chunk_grab(const ChunkQueue &cq, int &s_probe)
-{
-    const uint32_t home = sm_id() % (uint32_t)cq.nq;
-    int probe = s_probe;
-    int got = -1;
-    while (probe < cq.nq) {
-        uint32_t qi = home + (uint32_t)probe;
-        if (qi >= (uint32_t)cq.nq) qi -= (uint32_t)cq.nq;
-        const uint32_t c = atomicAdd(cq.queue + qi, 1u);
-        const long long chunk = (long long)qi * cq.per_queue + c;
-        if (c < (uint32_t)cq.per_queue && chunk < cq.nchunks) {
-            got = (int)chunk;
-            break;
-        }
-        ++probe;
-    }
-    s_probe = probe;
-    return got;
-}
-#endif
-
-template <class Body>
-__device__ __forceinline__ void for_each_chunk(const ChunkQueue &cq, Body body)
-{
-#if SPH_PP_SMQ
-    __shared__ int s_next, s_probe;
-    const bool queued = cq.queue != nullptr;
-    if (queued) {
-        if (threadIdx.x == 0) {
-            s_probe = 0;
-            s_next = chunk_grab(cq, s_probe);
-        }
-        __syncthreads();
-    }
-    for (;;) {
-        const int chunk = queued ? s_next : (int)blockIdx.x;
-        if (queued) __syncthreads();
-        if (chunk < 0) break;
-        if (queued && threadIdx.x == 0) s_next = chunk_grab(cq, s_probe);   // in flight while this chunk is worked on
-        body(chunk);
-        if (!queued) break;
-        __syncthreads();
-    }
-#else
-    (void)cq;
-    body((int)blockIdx.x);
-#endif
-}
-
-__device__ __forceinline__ int load_idx(const int32_t *p)
-{
-#if SPH_IDX_NOALLOC
-    int v;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-#else
-    return *p;
-#endif
-}
 
 
 __global__ void __launch_bounds__(kBlock)
@@ -329,8 +205,8 @@ gather_kernel(const __grid_constant__ sph_grid g, int n, const int32_t *__restri
     const size_t i = (size_t)perm[a];
     const double x = r[3 * i], y = r[3 * i + 1], z = r[3 * i + 2];
     const CellLoc c = locate(g, x, y, z);
-    store4(pos4 + kRowD * (size_t)a, x, y, z, m[i]);
-    store4(vel4 + kRowD * (size_t)a, v[3 * i], v[3 * i + 1], v[3 * i + 2], 0.0);
+    store4(pos4 + 4 * (size_t)a, x, y, z, m[i]);
+    store4(vel4 + 4 * (size_t)a, v[3 * i], v[3 * i + 1], v[3 * i + 2], 0.0);
     reinterpret_cast<float4 *>(rel4)[a] = make_float4(c.rx, c.ry, c.rz, __uint_as_float(c.interior ? 1u : 0u));
 }
 
@@ -590,21 +466,21 @@ __device__ __forceinline__ double density_row(const sph_grid &g, const double *_
     for (int st = 0; st < SPH_IDX_AHEAD; ++st)
 #pragma unroll
         for (int u = 0; u < kRowU; ++u)
-            jn[st][u] = st * kRowU + u < count ? load_idx(row + (size_t)(st * kRowU + u) * stride) : self;
+            jn[st][u] = st * kRowU + u < count ? row[(size_t)(st * kRowU + u) * stride] : self;
     for (int k0 = 0; k0 < count; k0 += kRowU) {
         double bx[kRowU], by[kRowU], bz[kRowU], bm[kRowU];
         int j[kRowU];
 #pragma unroll
         for (int u = 0; u < kRowU; ++u) {
             j[u] = jn[0][u];
-            load_row4(pos4 + kRowD * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
+            load4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
         }
 #pragma unroll
         for (int u = 0; u < kRowU; ++u) {
             const int kn = k0 + SPH_IDX_AHEAD * kRowU + u;
 #pragma unroll
             for (int st = 0; st + 1 < SPH_IDX_AHEAD; ++st) jn[st][u] = jn[st + 1][u];
-            jn[SPH_IDX_AHEAD - 1][u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
+            jn[SPH_IDX_AHEAD - 1][u] = kn < count ? row[(size_t)kn * stride] : self;
         }
 #pragma unroll
         for (int u = 0; u < kRowU; ++u) {
@@ -633,63 +509,6 @@ __device__ __forceinline__ double density_row(const sph_grid &g, const double *_
     return acc;
 }
 
-#if SPH_INTRA_SHFL
-// Density row, one neighbour per trip; every lane runs the warp's longest row because the shuffles need all lanes.
-// A neighbour j with j >> 5 == self >> 5 is the particle of lane j & 31 of this warp: its row (x y z m) is in that
-// lane's registers.  Other neighbours are gathered as in density_row, by the lanes that need them only.
-template <bool UNIFORM_H, bool WRAP>
-__device__ __forceinline__ double density_row_shfl(const sph_grid &g, const double *__restrict__ pos4,
-                                                   const int32_t *__restrict__ perm,
-                                                   const double *__restrict__ h_orig,
-                                                   const int32_t *__restrict__ row, int count, int orig, int self,
-                                                   double ax, double ay, double az, double am, double hinv, double qn)
-{
-    double acc = 0.0;
-    const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
-    const unsigned full = 0xffffffffu;
-    const int wid = self >> 5;
-    const int trips = __reduce_max_sync(full, count);
-    int jn0 = 0 < count ? load_idx(row) : self;
-    int jn1 = 1 < count ? load_idx(row + 32) : self;
-    for (int k = 0; k < trips; ++k) {
-        const int j = jn0;
-        jn0 = jn1;
-        jn1 = k + 2 < count ? load_idx(row + (size_t)(k + 2) * 32) : self;
-        const bool valid = k < count;
-        const bool intra = valid && (j >> 5) == wid;
-        double bx = ax, by = ay, bz = az, bm = 0.0;
-        if (valid && !intra) load_row4(pos4 + kRowD * (size_t)j, bx, by, bz, bm);
-        if (__any_sync(full, intra)) {
-            const int src = j & 31;
-            const double sx = __shfl_sync(full, ax, src), sy = __shfl_sync(full, ay, src);
-            const double sz = __shfl_sync(full, az, src), sm = __shfl_sync(full, am, src);
-            if (intra) { bx = sx; by = sy; bz = sz; bm = sm; }
-        }
-        double dx = bx - ax, dy = by - ay, dz = bz - az;
-        if (WRAP) {
-            dx = min_image(dx, g.box[0], hx);
-            dy = min_image(dy, g.box[1], hy);
-            dz = min_image(dz, g.box[2], hz);
-        }
-        const double rsq = rsq_exact(dx, dy, dz);
-        const double rr = sqrt(rsq);
-        double hi = hinv, q = qn;
-        if (!UNIFORM_H) {
-            const int oj = perm[j];
-            const double h = h_orig[oj < orig ? oj : orig];
-            hi = 1.0 / h;
-            q = lucy_norm3(h);
-        }
-        const double s = rr * hi;
-        if (s < 1.0 && valid) {
-            const double t = 1.0 - s;
-            acc += (q * (1.0 + 3.0 * s) * (t * t * t)) * bm;
-        }
-    }
-    return acc;
-}
-#endif
-
 // LPP lanes cooperate on one particle: lane q of the group takes neighbours q, q+LPP, ... of the
 // row, so that the lanes of a group gather consecutive rows (neighbours from one cell are
 // contiguous in the sorted arrays) and the per-lane trip counts even out; the partial sums are
@@ -702,17 +521,16 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
                const int32_t *__restrict__ cnt, const sph_status *__restrict__ status,
                const double *__restrict__ h_orig, sph_eos eos, int list_fresh, int long_range,
                double *__restrict__ rho_out, double *__restrict__ p_out, double *__restrict__ pco_out,
-               double *__restrict__ u_out, double *__restrict__ t_io, ChunkQueue cq)
+               double *__restrict__ u_out, double *__restrict__ t_io)
 {
-    for_each_chunk(cq, [&](int chunk) {
-    const int gt = chunk * kPPBlock + threadIdx.x;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int a = gt / LPP, q = gt % LPP;
     const bool active = a < n;
     double ax = 0, ay = 0, az = 0, am = 0;
     int count = 0, orig = 0;
     bool interior = true;
     if (active) {
-        load4(pos4 + kRowD * (size_t)a, ax, ay, az, am);
+        load4(pos4 + 4 * (size_t)a, ax, ay, az, am);
         count = min(cnt[a], K);
         orig = perm[a];
         interior = cell_is_interior(g, __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w));
@@ -724,14 +542,6 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
     const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K + q) * 32 + (a & 31);
     const int mine = count > q ? (count - q + LPP - 1) / LPP : 0;
     double sum;
-#if SPH_INTRA_SHFL
-    if (LPP == 1) {
-        const int self = active ? a : 0;
-        const int32_t *rowp = active ? row : nbr;
-        if (skip) sum = density_row_shfl<UNIFORM_H, false>(g, pos4, perm, h_orig, rowp, count, orig, self, ax, ay, az, am, hinv, qn);
-        else sum = density_row_shfl<UNIFORM_H, true>(g, pos4, perm, h_orig, rowp, count, orig, self, ax, ay, az, am, hinv, qn);
-    } else
-#endif
     if (skip) sum = density_row<UNIFORM_H, false>(g, pos4, perm, h_orig, row, (size_t)32 * LPP, mine, orig, a, ax, ay, az, hinv, qn);
     else sum = density_row<UNIFORM_H, true>(g, pos4, perm, h_orig, row, (size_t)32 * LPP, mine, orig, a, ax, ay, az, hinv, qn);
 #pragma unroll
@@ -749,8 +559,7 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
     pco_out[orig] = pco;
     u_out[orig] = u;
     t_io[orig] = (u + eos.adash * rho) / eos.kbdash;                        // properties.py:49,120
-    vel4[kRowD * (size_t)a + 3] = p / (rho * rho);                              // forces.py:353 operand
-    });
+    vel4[4 * (size_t)a + 3] = p / (rho * rho);                              // forces.py:353 operand
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -762,13 +571,13 @@ pressure_term_kernel(int n, int first_orig, const int32_t *__restrict__ perm, co
     const int o = perm[a];
     if (o < first_orig) return;
     const double d = rho[o];
-    vel4[kRowD * (size_t)a + 3] = press[o] / (d * d);
+    vel4[4 * (size_t)a + 3] = press[o] / (d * d);
 }
 
 struct ForceAcc { double ax, ay, az, du; };
 
-constexpr int kRowUF = SPH_ROW_UF;            // force: 8 doubles per neighbour, so a shorter stage
-constexpr int kRowUC = 2;                     // conduction (not register-capped)
+constexpr int kRowUF = SPH_ROW_UF;   // force: 8 doubles per neighbour, so a shorter stage
+constexpr int kRowUC = 2;            // conduction (not register-capped)
 
 template <bool UNIFORM_H, bool WRAP>
 __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *__restrict__ pos4,
@@ -782,63 +591,28 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
 {
     ForceAcc f = {0.0, 0.0, 0.0, 0.0};
     const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
-#if SPH_ROW_PIPE
-    // double-buffered rows: the rows of stage k0 + kRowUF are requested before stage k0 is evaluated
-    int jn[SPH_IDX_AHEAD_F][kRowUF];          // indices of the stages after the one whose rows are in flight
-    double bx[kRowUF], by[kRowUF], bz[kRowUF], bm[kRowUF], wx[kRowUF], wy[kRowUF], wz[kRowUF], Aj[kRowUF];
-    int j[kRowUF];
-#pragma unroll
-    for (int u = 0; u < kRowUF; ++u) j[u] = u < count ? load_idx(row + (size_t)u * stride) : self;
+    int jn[SPH_IDX_AHEAD_F][kRowUF];       // indices of the next SPH_IDX_AHEAD_F stages
 #pragma unroll
     for (int st = 0; st < SPH_IDX_AHEAD_F; ++st)
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u)
-            jn[st][u] = (st + 1) * kRowUF + u < count ? load_idx(row + (size_t)((st + 1) * kRowUF + u) * stride) : self;
-#pragma unroll
-    for (int u = 0; u < kRowUF; ++u) {
-        load_row4(pos4 + kRowD * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
-        load_row4(vel4 + kRowD * (size_t)j[u], wx[u], wy[u], wz[u], Aj[u]);
-    }
-    for (int k0 = 0; k0 < count; k0 += kRowUF) {
-        double nbx[kRowUF], nby[kRowUF], nbz[kRowUF], nbm[kRowUF], nwx[kRowUF], nwy[kRowUF], nwz[kRowUF], nAj[kRowUF];
-        int nj[kRowUF];
-#pragma unroll
-        for (int u = 0; u < kRowUF; ++u) {
-            nj[u] = jn[0][u];
-            load_row4(pos4 + kRowD * (size_t)nj[u], nbx[u], nby[u], nbz[u], nbm[u]);
-            load_row4(vel4 + kRowD * (size_t)nj[u], nwx[u], nwy[u], nwz[u], nAj[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < kRowUF; ++u) {
-            const int kn = k0 + (SPH_IDX_AHEAD_F + 1) * kRowUF + u;
-#pragma unroll
-            for (int st = 0; st + 1 < SPH_IDX_AHEAD_F; ++st) jn[st][u] = jn[st + 1][u];
-            jn[SPH_IDX_AHEAD_F - 1][u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
-        }
-#else
-    int jn[SPH_IDX_AHEAD_F][kRowUF];          // indices of the next SPH_IDX_AHEAD_F stages
-#pragma unroll
-    for (int st = 0; st < SPH_IDX_AHEAD_F; ++st)
-#pragma unroll
-        for (int u = 0; u < kRowUF; ++u)
-            jn[st][u] = st * kRowUF + u < count ? load_idx(row + (size_t)(st * kRowUF + u) * stride) : self;
+            jn[st][u] = st * kRowUF + u < count ? row[(size_t)(st * kRowUF + u) * stride] : self;
     for (int k0 = 0; k0 < count; k0 += kRowUF) {
         double bx[kRowUF], by[kRowUF], bz[kRowUF], bm[kRowUF], wx[kRowUF], wy[kRowUF], wz[kRowUF], Aj[kRowUF];
         int j[kRowUF];
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
             j[u] = jn[0][u];
-            load_row4(pos4 + kRowD * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
-            load_row4(vel4 + kRowD * (size_t)j[u], wx[u], wy[u], wz[u], Aj[u]);
+            load4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
+            load4(vel4 + 4 * (size_t)j[u], wx[u], wy[u], wz[u], Aj[u]);
         }
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
             const int kn = k0 + SPH_IDX_AHEAD_F * kRowUF + u;
 #pragma unroll
             for (int st = 0; st + 1 < SPH_IDX_AHEAD_F; ++st) jn[st][u] = jn[st + 1][u];
-            jn[SPH_IDX_AHEAD_F - 1][u] = kn < count ? load_idx(row + (size_t)kn * stride) : self;
+            jn[SPH_IDX_AHEAD_F - 1][u] = kn < count ? row[(size_t)kn * stride] : self;
         }
-#endif
 #pragma unroll
         for (int u = 0; u < kRowUF; ++u) {
             // Pair (i<j in original order) contributes +a to i and -a to j with dr = r_j - r_i.
@@ -873,159 +647,9 @@ __device__ __forceinline__ ForceAcc force_row(const sph_grid &g, const double *_
                 f.du += (0.5 * dot) * bm[u];
             }
         }
-#if SPH_ROW_PIPE
-#pragma unroll
-        for (int u = 0; u < kRowUF; ++u) {
-            j[u] = nj[u];
-            bx[u] = nbx[u]; by[u] = nby[u]; bz[u] = nbz[u]; bm[u] = nbm[u];
-            wx[u] = nwx[u]; wy[u] = nwy[u]; wz[u] = nwz[u]; Aj[u] = nAj[u];
-        }
-#endif
     }
     return f;
 }
-
-#if SPH_INTRA_SHFL
-// Force row with in-warp neighbours taken by shuffle (see density_row_shfl): eight doubles per neighbour come from
-// the registers of lane j & 31 when j is a particle of this warp, from two gathered rows otherwise.
-template <bool UNIFORM_H, bool WRAP>
-__device__ __forceinline__ ForceAcc force_row_shfl(const sph_grid &g, const double *__restrict__ pos4,
-                                                   const double *__restrict__ vel4,
-                                                   const int32_t *__restrict__ perm,
-                                                   const double *__restrict__ h_orig,
-                                                   const int32_t *__restrict__ row, int count, int orig, int self,
-                                                   double px, double py, double pz, double pm, double vx, double vy,
-                                                   double vz, double Ai, double hinv, double c2, double fcutsq,
-                                                   bool two_d)
-{
-    ForceAcc f = {0.0, 0.0, 0.0, 0.0};
-    const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
-    const unsigned full = 0xffffffffu;
-    const int wid = self >> 5;
-    const int trips = __reduce_max_sync(full, count);
-    int jn0 = 0 < count ? load_idx(row) : self;
-    int jn1 = 1 < count ? load_idx(row + 32) : self;
-    for (int k = 0; k < trips; ++k) {
-        const int j = jn0;
-        jn0 = jn1;
-        jn1 = k + 2 < count ? load_idx(row + (size_t)(k + 2) * 32) : self;
-        const bool valid = k < count;
-        const bool intra = valid && (j >> 5) == wid;
-        double bx = px, by = py, bz = pz, bm = 0.0, wx = vx, wy = vy, wz = vz, Aj = Ai;
-        if (valid && !intra) {
-            load_row4(pos4 + kRowD * (size_t)j, bx, by, bz, bm);
-            load_row4(vel4 + kRowD * (size_t)j, wx, wy, wz, Aj);
-        }
-        if (__any_sync(full, intra)) {
-            const int src = j & 31;
-            const double s0 = __shfl_sync(full, px, src), s1 = __shfl_sync(full, py, src);
-            const double s2 = __shfl_sync(full, pz, src), s3 = __shfl_sync(full, pm, src);
-            const double s4 = __shfl_sync(full, vx, src), s5 = __shfl_sync(full, vy, src);
-            const double s6 = __shfl_sync(full, vz, src), s7 = __shfl_sync(full, Ai, src);
-            if (intra) { bx = s0; by = s1; bz = s2; bm = s3; wx = s4; wy = s5; wz = s6; Aj = s7; }
-        }
-        double dx = bx - px, dy = by - py, dz = bz - pz;
-        if (WRAP) {
-            dx = min_image(dx, g.box[0], hx);
-            dy = min_image(dy, g.box[1], hy);
-            dz = min_image(dz, g.box[2], hz);
-        }
-        const double rsq = rsq_exact(dx, dy, dz);
-        const double rr = sqrt(rsq);
-        double hi = hinv, cc = c2;
-        if (!UNIFORM_H) {
-            const int oj = perm[j];
-            const double h = h_orig[oj < orig ? oj : orig];
-            hi = 1.0 / h;
-            cc = -12.0 * lucy_norm3(h) * hi * hi;
-        }
-        const double s = rr * hi;
-        if (s < 1.0 && rr * rr <= fcutsq && valid) {
-            const double t = 1.0 - s;
-            const double fac = (cc * (t * t)) * (Ai + Aj);
-            const double gx = fac * dx, gy = fac * dy, gz = two_d ? 0.0 : fac * dz;
-            f.ax += gx;
-            f.ay += gy;
-            f.az += gz;
-            const double dot = gx * (wx - vx) + gy * (wy - vy) + gz * (wz - vz);
-            f.du += (0.5 * dot) * bm;
-        }
-    }
-    return f;
-}
-#endif
-
-#if SPH_FORCE_PAIRLOAD
-// Force row with lane-pair gathers (one lane per particle as before).  L1 retires one wavefront per 128-byte line
-// a request touches; a lane loading the two 32-byte halves of its neighbour's state costs two lines.  Here the lanes
-// 2i and 2i+1 read, in one request, the position half (even lane) and the velocity half (odd lane) of the SAME
-// 64-byte row: first the even lane's neighbour, then the odd lane's.  Each lane then holds one half of its own
-// neighbour and one half of its partner's, and a shuffle swaps the foreign halves.  Every lane runs the warp's
-// longest row (the shuffles need all lanes); trips past a lane's own count gather its own row and add nothing.
-// The arithmetic is that of force_row, term by term.
-template <bool UNIFORM_H, bool WRAP>
-__device__ __forceinline__ ForceAcc force_row_pair(const sph_grid &g, const double *__restrict__ rows8,
-                                                   const int32_t *__restrict__ perm,
-                                                   const double *__restrict__ h_orig,
-                                                   const int32_t *__restrict__ row, int count, int orig, int self,
-                                                   double px, double py, double pz, double vx, double vy, double vz,
-                                                   double Ai, double hinv, double c2, double fcutsq, bool two_d)
-{
-    ForceAcc f = {0.0, 0.0, 0.0, 0.0};
-    const double hx = g.box[0] / 2., hy = g.box[1] / 2., hz = g.box[2] / 2.;
-    const unsigned full = 0xffffffffu;
-    const bool odd = (threadIdx.x & 1) != 0;
-    const size_t half = odd ? 4 : 0;
-    const int trips = __reduce_max_sync(full, count);
-    int jn0 = 0 < count ? load_idx(row) : self;
-    int jn1 = 1 < count ? load_idx(row + 32) : self;
-    for (int k = 0; k < trips; ++k) {
-        const int jme = jn0;
-        jn0 = jn1;
-        jn1 = k + 2 < count ? load_idx(row + (size_t)(k + 2) * 32) : self;
-        const int jpartner = __shfl_xor_sync(full, jme, 1);
-        const int je = odd ? jpartner : jme;          // neighbour of the pair's even lane
-        const int jo = odd ? jme : jpartner;          // neighbour of the pair's odd lane
-        double a0, a1, a2, a3, b0, b1, b2, b3;
-        load_row4(rows8 + 8 * (size_t)je + half, a0, a1, a2, a3);     // even lane: position of je, odd lane: velocity of je
-        load_row4(rows8 + 8 * (size_t)jo + half, b0, b1, b2, b3);     // even lane: position of jo, odd lane: velocity of jo
-        // the even lane lacks the velocity of je (the odd lane's a), the odd lane the position of jo (the even lane's b)
-        const double r0 = __shfl_xor_sync(full, odd ? a0 : b0, 1);
-        const double r1 = __shfl_xor_sync(full, odd ? a1 : b1, 1);
-        const double r2 = __shfl_xor_sync(full, odd ? a2 : b2, 1);
-        const double r3 = __shfl_xor_sync(full, odd ? a3 : b3, 1);
-        const double bx = odd ? r0 : a0, by = odd ? r1 : a1, bz = odd ? r2 : a2, bm = odd ? r3 : a3;
-        const double wx = odd ? b0 : r0, wy = odd ? b1 : r1, wz = odd ? b2 : r2, Aj = odd ? b3 : r3;
-        double dx = bx - px, dy = by - py, dz = bz - pz;
-        if (WRAP) {
-            dx = min_image(dx, g.box[0], hx);
-            dy = min_image(dy, g.box[1], hy);
-            dz = min_image(dz, g.box[2], hz);
-        }
-        const double rsq = rsq_exact(dx, dy, dz);
-        const double rr = sqrt(rsq);
-        double hi = hinv, cc = c2;
-        if (!UNIFORM_H) {
-            const int oj = perm[jme];
-            const double h = h_orig[oj < orig ? oj : orig];
-            hi = 1.0 / h;
-            cc = -12.0 * lucy_norm3(h) * hi * hi;
-        }
-        const double s = rr * hi;
-        if (s < 1.0 && rr * rr <= fcutsq && k < count) {
-            const double t = 1.0 - s;
-            const double fac = (cc * (t * t)) * (Ai + Aj);
-            const double gx = fac * dx, gy = fac * dy, gz = two_d ? 0.0 : fac * dz;
-            f.ax += gx;
-            f.ay += gy;
-            f.az += gz;
-            const double dot = gx * (wx - vx) + gy * (wy - vy) + gz * (wz - vz);
-            f.du += (0.5 * dot) * bm;
-        }
-    }
-    return f;
-}
-#endif
 
 template <bool UNIFORM_H, int LPP>
 __global__ void __launch_bounds__(kPPBlock, SPH_FORCE_MINB)
@@ -1034,18 +658,17 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
              const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
              const int32_t *__restrict__ cnt, const sph_status *__restrict__ status,
              const double *__restrict__ h_orig, int list_fresh, double fcutsq, int dim,
-             double *__restrict__ vdot, double *__restrict__ udot, ChunkQueue cq)
+             double *__restrict__ vdot, double *__restrict__ udot)
 {
-    for_each_chunk(cq, [&](int chunk) {
-    const int gt = chunk * kPPBlock + threadIdx.x;
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int a = gt / LPP, q = gt % LPP;
     const bool active = a < n;
     double px = 0, py = 0, pz = 0, pm = 0, vx = 0, vy = 0, vz = 0, Ai = 0;
     int count = 0, orig = 0;
     bool interior = true;
     if (active) {
-        load4(pos4 + kRowD * (size_t)a, px, py, pz, pm);
-        load4(vel4 + kRowD * (size_t)a, vx, vy, vz, Ai);
+        load4(pos4 + 4 * (size_t)a, px, py, pz, pm);
+        load4(vel4 + 4 * (size_t)a, vx, vy, vz, Ai);
         count = min(cnt[a], K);
         orig = perm[a];
         interior = cell_is_interior(g, __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w));
@@ -1057,21 +680,6 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
     const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K + q) * 32 + (a & 31);
     const int mine = count > q ? (count - q + LPP - 1) / LPP : 0;
     ForceAcc f;
-#if SPH_INTRA_SHFL
-    if (LPP == 1) {
-        const int self = active ? a : 0;
-        const int32_t *rowp = active ? row : nbr;
-        if (skip) f = force_row_shfl<UNIFORM_H, false>(g, pos4, vel4, perm, h_orig, rowp, count, orig, self, px, py, pz, pm, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
-        else f = force_row_shfl<UNIFORM_H, true>(g, pos4, vel4, perm, h_orig, rowp, count, orig, self, px, py, pz, pm, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
-    } else
-#elif SPH_FORCE_PAIRLOAD
-    if (LPP == 1) {
-        const int self = active ? a : 0;                // lanes past the end still gather (a valid row) with the others
-        const int32_t *rowp = active ? row : nbr;
-        if (skip) f = force_row_pair<UNIFORM_H, false>(g, pos4, perm, h_orig, rowp, count, orig, self, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
-        else f = force_row_pair<UNIFORM_H, true>(g, pos4, perm, h_orig, rowp, count, orig, self, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
-    } else
-#endif
     if (skip) f = force_row<UNIFORM_H, false>(g, pos4, vel4, perm, h_orig, row, (size_t)32 * LPP, mine, orig, a, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
     else f = force_row<UNIFORM_H, true>(g, pos4, vel4, perm, h_orig, row, (size_t)32 * LPP, mine, orig, a, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
 #pragma unroll
@@ -1088,7 +696,6 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
     vdot[3 * (size_t)orig + 1] += f.ay;
     vdot[3 * (size_t)orig + 2] += f.az;
     udot[orig] += f.du;
-    });
 }
 
 // ------------------------------------------------------------------ heat conduction (c_forces.pyx:196-239)
@@ -1123,7 +730,7 @@ __device__ __forceinline__ double conduction_row(const sph_grid &g, const double
 #pragma unroll
         for (int u = 0; u < kRowUC; ++u) {
             j[u] = jn[u];
-            load4(pos4 + kRowD * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
+            load4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
             load4(aux4 + 4 * (size_t)j[u], ex[u], ey[u], ez[u], ew[u]);
         }
 #pragma unroll
@@ -1173,7 +780,7 @@ conduction_kernel(const __grid_constant__ sph_grid g, int n, int K, const double
     int count = 0, orig = 0;
     bool interior = true;
     if (active) {
-        load4(pos4 + kRowD * (size_t)a, px, py, pz, pm);
+        load4(pos4 + 4 * (size_t)a, px, py, pz, pm);
         load4(aux4 + 4 * (size_t)a, qx, qy, qz, qw);
         count = min(cnt[a], K);
         orig = perm[a];
@@ -1473,38 +1080,6 @@ inline int launch_status()
     return e == cudaSuccess ? SPH_OK : (int)e;
 }
 
-// Diagnostic (SPH_SORT_ROWS in the environment), run after the neighbour pass.  1: rewrite every ELL row in ascending
-// order of the sorted neighbour index, to measure what a common sweep order of the lanes of a warp is worth to the
-// gathers of the density / force passes.  2: stable partition, the neighbours inside the particle's own warp first
-// (for builds with SPH_INTRA_SHFL).  Not tuned: one thread per row, local-memory copy.
-__global__ void __launch_bounds__(kBlock)
-row_sort_kernel(int n, int K, int32_t *__restrict__ nbr, const int32_t *__restrict__ cnt, int mode)
-{
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= n) return;
-    const int c = min(cnt[a], K);
-    constexpr int kMax = 96;
-    if (c < 2 || c > kMax) return;
-    int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
-    int32_t v[kMax];
-    for (int k = 0; k < c; ++k) v[k] = row[(size_t)k * 32];
-    if (mode == 2) {                        // stable partition: neighbours inside this particle's warp first
-        int w = 0;
-        for (int k = 0; k < c; ++k)
-            if ((v[k] >> 5) == (a >> 5)) row[(size_t)(w++) * 32] = v[k];
-        for (int k = 0; k < c; ++k)
-            if ((v[k] >> 5) != (a >> 5)) row[(size_t)(w++) * 32] = v[k];
-        return;
-    }
-    for (int i = 1; i < c; ++i) {
-        const int32_t x = v[i];
-        int j = i - 1;
-        while (j >= 0 && v[j] > x) { v[j + 1] = v[j]; --j; }
-        v[j + 1] = x;
-    }
-    for (int k = 0; k < c; ++k) row[(size_t)k * 32] = v[k];
-}
-
 // Lanes cooperating on one particle in the density / force passes.  Measured on B200 (256^3):
 // 1 lane per particle is fastest (density 2.10 ms; 2 lanes 2.52, 4 lanes 3.69, 8 lanes 5.23):
 // splitting a row over lanes makes the index loads touch LPP lines per request and buys nothing
@@ -1535,45 +1110,6 @@ int sm_count()
 }
 
 constexpr double kCellTarget = 8.0;    // particles per cell the planner widens sparse grids towards (0: off)
-constexpr int kQueueSlots = 1024;     // uint32 slots at the head of sph_buffers.scan_tmp (free after the cell scan)
-
-// Launch geometry of a per-particle pass.  Default: one block per chunk of kPPBlock lanes.  With SPH_PP_SMQ the
-// grid is persistent (resident blocks per SM x SMs) and the chunks are dealt to per-SM queues kept in scan_tmp.
-ChunkQueue chunk_plan(const sph_buffers *b, int lpp, const void *kernel, cudaStream_t s, int &grid)
-{
-    ChunkQueue cq = {nullptr, 0, 0, 0};
-    cq.nchunks = blocks_for((int64_t)b->n * lpp, kPPBlock);
-    grid = cq.nchunks;
-#if SPH_PP_MAXL1
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-#endif
-#if SPH_PP_SMQ
-    const int nsm = sm_count();
-    static const void *seen[32];
-    static int seen_blocks[32], n_seen = 0;
-    int per_sm = 0;
-    for (int i = 0; i < n_seen; ++i)
-        if (seen[i] == kernel) per_sm = seen_blocks[i];
-    if (!per_sm) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kPPBlock, 0);
-        if (per_sm > 0 && n_seen < 32) {
-            seen[n_seen] = kernel;
-            seen_blocks[n_seen++] = per_sm;
-        }
-    }
-    if (b->scan_tmp && nsm <= kQueueSlots && per_sm > 0 && cq.nchunks > 2 * nsm * per_sm) {
-        cq.queue = b->scan_tmp;
-        cq.nq = nsm;
-        cq.per_queue = (cq.nchunks + nsm - 1) / nsm;
-        grid = nsm * per_sm;
-        cudaMemsetAsync(cq.queue, 0, sizeof(uint32_t) * (size_t)nsm, s);
-    }
-#else
-    (void)kernel;
-    (void)s;
-#endif
-    return cq;
-}
 
 }  // namespace
 
@@ -1584,10 +1120,8 @@ const char *sph_version(void) { return "pyticles_b200 0.2 (sm_100a, abi 2)"; }
 
 int64_t sph_scan_tmp_elems(uint32_t ncode)
 {
-    return ((int64_t)ncode + kScanTile - 1) / kScanTile + 2 + kQueueSlots;
+    return ((int64_t)ncode + kScanTile - 1) / kScanTile + 2;
 }
-
-int sph_row_doubles(void) { return kRowD; }
 
 int64_t sph_nbr_elems(int32_t n, int32_t max_nbrs)
 {
@@ -1793,7 +1327,6 @@ int sph_gather(const sph_grid *g, const sph_buffers *b, const double *d_r, const
                const double *d_m, void *stream)
 {
     if (!g || !b || !d_r || !d_v || !d_m || !b->pos4 || !b->vel4 || !b->rel4 || !b->perm) return SPH_E_BADARG;
-    if (kRowD == 8 && b->vel4 != b->pos4 + 4) return SPH_E_BADARG;      // interleaved rows: see sph_row_doubles()
     if (b->n > 0)
         gather_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
             *g, b->n, b->perm, d_r, d_v, d_m, b->pos4, b->vel4, b->rel4);
@@ -1836,15 +1369,7 @@ int sph_nlist_build(const sph_grid *g, const sph_buffers *b, void *stream)
         const int rc = sph_tiles::launch_list(g, b, s);
         if (rc != SPH_OK) return rc;
     }
-    const int rc = nlist_general(g, b, tiles ? 1 : 0, s);
-    static int sort_rows = -1;
-    if (sort_rows < 0) {
-        const char *e = getenv("SPH_SORT_ROWS");
-        sort_rows = e ? atoi(e) : 0;
-    }
-    if (rc == SPH_OK && sort_rows)
-        row_sort_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, s>>>(b->n, b->max_nbrs, b->nbr, b->cnt, sort_rows);
-    return rc;
+    return nlist_general(g, b, tiles ? 1 : 0, s);
 }
 
 int sph_density_eos(const sph_grid *g, const sph_buffers *b, const sph_eos *eos,
@@ -1857,13 +1382,9 @@ int sph_density_eos(const sph_grid *g, const sph_buffers *b, const sph_eos *eos,
     cudaStream_t s = (cudaStream_t)stream;
     const int lpp = lanes_per_particle();
 #define SPH_LAUNCH_DENSITY(U, L)                                                                              \
-    do {                                                                                                         \
-        int grid = 0;                                                                                         \
-        const ChunkQueue cq = chunk_plan(b, L, (const void *)density_kernel<U, L>, s, grid);                  \
-        density_kernel<U, L><<<grid, kPPBlock, 0, s>>>(                                                       \
-            *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig,   \
-            *eos, list_fresh, use_hlr, d_rho, d_p, d_pco, d_u, d_t, cq);                                      \
-    } while (0)
+    density_kernel<U, L><<<blocks_for((int64_t)b->n * L, kPPBlock), kPPBlock, 0, s>>>(                        \
+        *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig, *eos, \
+        list_fresh, use_hlr, d_rho, d_p, d_pco, d_u, d_t)
     if (h_uniform) {
         if (lpp == 1) SPH_LAUNCH_DENSITY(true, 1);
         else if (lpp == 2) SPH_LAUNCH_DENSITY(true, 2);
@@ -1891,13 +1412,9 @@ int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, co
     const int lpp = lanes_per_particle();
 
 #define SPH_LAUNCH_FORCE(U, L)                                                                                 \
-    do {                                                                                                          \
-        int grid = 0;                                                                                          \
-        const ChunkQueue cq = chunk_plan(b, L, (const void *)force_kernel<U, L>, s, grid);                     \
-        force_kernel<U, L><<<grid, kPPBlock, 0, s>>>(                                                          \
-            *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig,    \
-            list_fresh, fcutsq, dim, d_vdot, d_udot, cq);                                                      \
-    } while (0)
+    force_kernel<U, L><<<blocks_for((int64_t)b->n * L, kPPBlock), kPPBlock, 0, s>>>(                           \
+        *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig,        \
+        list_fresh, fcutsq, dim, d_vdot, d_udot)
     if (h_uniform) {
         if (lpp == 1) SPH_LAUNCH_FORCE(true, 1);
         else if (lpp == 2) SPH_LAUNCH_FORCE(true, 2);

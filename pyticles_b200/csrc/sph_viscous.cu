@@ -34,8 +34,8 @@ volume_term_kernel(int n, const int32_t *__restrict__ perm, const double *__rest
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
     double x, y, z, m, vx, vy, vz, w;
-    load4(pos4 + kRowD * (size_t)a, x, y, z, m);
-    load4(vel4 + kRowD * (size_t)a, vx, vy, vz, w);
+    load4(pos4 + 4 * (size_t)a, x, y, z, m);
+    load4(vel4 + 4 * (size_t)a, vx, vy, vz, w);
     store4(aux4 + 4 * (size_t)a, vx, vy, vz, m / rho[perm[a]]);
 }
 
@@ -87,7 +87,7 @@ __device__ __forceinline__ void gradv_row(const sph_grid &g, const double *__res
 #pragma unroll
         for (int u = 0; u < kVU; ++u) {
             j[u] = jn[u];
-            load4(pos4 + kRowD * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
+            load4(pos4 + 4 * (size_t)j[u], bx[u], by[u], bz[u], bm[u]);
             load4(aux4 + 4 * (size_t)j[u], wx[u], wy[u], wz[u], ww[u]);
         }
 #pragma unroll
@@ -125,7 +125,7 @@ gradv_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
     int count = 0, orig = 0;
     bool interior = true;
     if (active) {
-        load4(pos4 + kRowD * (size_t)a, px, py, pz, pm);
+        load4(pos4 + 4 * (size_t)a, px, py, pz, pm);
         load4(aux4 + 4 * (size_t)a, vx, vy, vz, vw);
         count = min(cnt[a], K);
         orig = perm[a];
@@ -184,8 +184,8 @@ __device__ __forceinline__ VAcc viscous_row(const sph_grid &g, const double *__r
     for (int k = 0; k < count; ++k) {
         const int j = jn;
         double bx, by, bz, bm, wx, wy, wz, ww, t0, t1, t2, t3, t4, t5, t6, t7;
-        load4(pos4 + kRowD * (size_t)j, bx, by, bz, bm);
-        load4(vel4 + kRowD * (size_t)j, wx, wy, wz, ww);
+        load4(pos4 + 4 * (size_t)j, bx, by, bz, bm);
+        load4(vel4 + 4 * (size_t)j, wx, wy, wz, ww);
         load4(aux8 + 8 * (size_t)j, t0, t1, t2, t3);
         load4(aux8 + 8 * (size_t)j + 4, t4, t5, t6, t7);
         jn = k + 1 < count ? row[(size_t)(k + 1) * 32] : self;
@@ -222,8 +222,8 @@ viscous_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
     int count = 0, orig = 0;
     bool interior = true;
     if (active) {
-        load4(pos4 + kRowD * (size_t)a, px, py, pz, pm);
-        load4(vel4 + kRowD * (size_t)a, vx, vy, vz, vw);
+        load4(pos4 + 4 * (size_t)a, px, py, pz, pm);
+        load4(vel4 + 4 * (size_t)a, vx, vy, vz, vw);
         load4(aux8 + 8 * (size_t)a, S[0], S[1], S[2], S[3]);
         load4(aux8 + 8 * (size_t)a + 4, S[4], S[5], s6, s7);
         count = min(cnt[a], K);

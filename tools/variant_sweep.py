@@ -33,9 +33,6 @@ VARIANTS = {
     "default": [],
     # first sweep (profiles/r1f_variant_sweep_gen1.txt): around the r1e defaults
     "base": _v(R1E),
-    "noalloc": _v(R1E, SPH_IDX_NOALLOC=1),
-    "keep": _v(R1E, SPH_ROW_KEEP=1),
-    "noalloc_keep": _v(R1E, SPH_IDX_NOALLOC=1, SPH_ROW_KEEP=1),
     "ahead2": _v(R1E, SPH_IDX_AHEAD=2),
     "b128": _v(R1E, SPH_PP_BLOCK=128),
     "b128_r72_80": _v(R1E, SPH_PP_BLOCK=128, SPH_DENS_MINB=7, SPH_FORCE_MINB=6),
@@ -43,28 +40,16 @@ VARIANTS = {
     "u2_uf1_b128_r48_72": _v(R1E, SPH_ROW_U=2, SPH_ROW_UF=1, SPH_PP_BLOCK=128, SPH_DENS_MINB=10, SPH_FORCE_MINB=7),
     "u4_uf1_b128_r72_72_ahead2": _v(W),
     "u6_uf3": _v(R1E, SPH_ROW_U=6, SPH_ROW_UF=3),
-    "b128_r72_80_noalloc_ahead2": _v(R1E, SPH_PP_BLOCK=128, SPH_DENS_MINB=7, SPH_FORCE_MINB=6, SPH_IDX_NOALLOC=1,
-                                     SPH_IDX_AHEAD=2),
     "b512": _v(R1E, SPH_PP_BLOCK=512),
     "b64": _v(R1E, SPH_PP_BLOCK=64),
     # second sweep (profiles/r1f_variant_sweep_gen2.txt): on top of the first sweep's winner
     "w": _v(W),
-    "w_smq": _v(W, SPH_PP_SMQ=1),
-    "w_smq_maxl1": _v(W, SPH_PP_SMQ=1, SPH_PP_MAXL1=1),
-    "w_maxl1": _v(W, SPH_PP_MAXL1=1),
     "w_f_ahead3": _v(W, SPH_IDX_AHEAD_F=3),
     "w_f_ahead4": _v(W, SPH_IDX_AHEAD_F=4),
-    "w_f_pipe_r80": _v(W, SPH_FORCE_MINB=6, SPH_ROW_PIPE=1),
     "w_f_r64": _v(W, SPH_FORCE_MINB=8),
-    "base_smq": _v(R1E, SPH_PP_SMQ=1),
-    # interleaved 64-byte rows and lane-pair gathers in the force pass
-    "w_stride8": _v(W, SPH_ROW_STRIDE=8),
-    "w_pairload": _v(W, SPH_ROW_STRIDE=8, SPH_FORCE_PAIRLOAD=1),
-    # in-warp neighbours by shuffle (run with SPH_SORT_ROWS=2 in the environment to list them first; the sums then run
-    # in another order, so the digest differs from the default build in the last bits)
-    "w_intra": _v(W, SPH_INTRA_SHFL=1),
-    "w_intra_d8": _v(W, SPH_INTRA_SHFL=1, SPH_DENS_MINB=8),
 }
+# The other rows of the r1f sweep tables (noalloc, keep, *_smq, *_maxl1, w_f_pipe_r80, w_stride8, w_pairload, w_intra)
+# were variants whose code was removed after they lost; they can be rebuilt from commit dac84c7.
 
 
 def lib_path(name):
