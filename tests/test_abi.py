@@ -137,3 +137,21 @@ def test_fails_loudly_without_extension_or_gpu(lib, monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", os.path.join(ROOT, "pyticles_b200", "does_not_exist.so"))
     with pytest.raises(_lib.SphError):
         _lib.load()
+
+
+def test_variant_sweep_flags_exist_in_the_source():
+    """tools/variant_sweep.py only names tunables the kernels file still has (a stale -D would silently
+    time the default build under another name)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("variant_sweep", os.path.join(ROOT, "tools", "variant_sweep.py"))
+    vs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vs)
+    src = open(os.path.join(ROOT, "pyticles_b200", "csrc", "sph_kernels.cu")).read()
+    assert vs.VARIANTS["default"] == []
+    for name, flags in vs.VARIANTS.items():
+        for f in flags:
+            macro = f[2:].split("=")[0]
+            assert re.search(r"#ifndef %s\b" % macro, src), (name, macro)
+    # the defaults compiled into the library are the sweep's winner
+    for macro, val in vs.W.items():
+        assert re.search(r"#define %s %s\b" % (macro, val), src), (macro, val)
