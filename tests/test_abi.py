@@ -155,3 +155,30 @@ def test_variant_sweep_flags_exist_in_the_source():
     # the defaults compiled into the library are the sweep's winner
     for macro, val in vs.W.items():
         assert re.search(r"#define %s %s\b" % (macro, val), src), (macro, val)
+
+
+def test_header_is_plain_c_and_links(tmp_path, lib):
+    """include/pyticles_b200.h compiles as C99 (no C++, no torch types) and a C program links against the
+    library and calls a host-only entry point -- what a cgo / JNI / ctypes binding relies on."""
+    import shutil
+    import subprocess
+    from pyticles_b200 import _lib
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "t.c"
+    src.write_text('#include <stdio.h>\n#include "pyticles_b200.h"\n'
+                   'int main(void) {\n'
+                   '    double box[3] = {20., 20., 20.};\n'
+                   '    sph_grid g;\n'
+                   '    int rc = sph_grid_plan(box, 2.0, 1.0, 0, 0, 0, &g);\n'
+                   '    printf("%d %d %s\\n", rc, (int)g.nc[0], sph_version());\n'
+                   '    return rc;\n}\n')
+    exe = tmp_path / "t"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", libdir, "-l:" + os.path.basename(_lib.LIB_PATH),
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rc, nc, ver = out.stdout.split(None, 2)
+    assert rc == "0" and int(nc) == 8 and "sm_100a" in ver
