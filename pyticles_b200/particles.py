@@ -13,7 +13,7 @@ box.apply -> thermostat.  Refinement/amalgamation (check_refine, split, amalgama
 experimental 2-D code paths switched off in every shipped script (particles.py:55-57) and
 are not provided.
 """
-from time import time
+from time import time as _wall
 
 import numpy as np
 import torch
@@ -31,6 +31,16 @@ VMAX = 0.1
 ADVECTIVE = False
 SPROPS = False
 FUSED = False            # SmoothParticleSystem.update: improved Euler without the [11, maxn] state matrices
+TIMING_SYNC = False      # True: synchronise the device before every clock read, so that p.timing holds device times
+                         # (a bspana_profile.py-style run); False: the reference's plain wall-clock deltas, which on an
+                         # asynchronous device are enqueue times
+
+
+def time():
+    """Clock of the p.timing entries (particles.py:163-169,474-493,552-567)."""
+    if TIMING_SYNC and torch.cuda.is_available():
+        torch.cuda.synchronize()
+    return _wall()
 DEVICE = "cuda"
 
 
