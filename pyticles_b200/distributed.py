@@ -431,6 +431,90 @@ class SlabSphEvaluator(object):
         return {"ms": t0.elapsed_time(t1), "steps": steps, "h2d": int(tot[0]), "d2h": int(tot[1])}
 
 
+class SlabStepper(object):
+    """Time stepping of a slab-decomposed system: what SmoothParticleSystem.update does (particles.py:459-494:
+    improved Euler of integrator.py:44-59 over r, v, u, then box.apply, then the scaling thermostat of
+    particles.py:450-457) with the particles spread over the ranks.
+
+    `sim` is a SlabSphEvaluator (or anything with its storage protocol: `dec`, `n_owned`, `S` with the owned
+    particles in front, `rows()`, `_load_rows(rows)`, `evaluate()`).  The predictor can carry a particle across
+    a slab face, and the second stage has to find it on the rank that owns its new cell layer: the stage-1 data
+    the corrector needs (start state, first-stage derivatives) travel with the particle through `migrate`, as extra
+    columns behind the NCOL state columns.  Like the reference's state vector (particles.py:538-540: zero state
+    derivatives for rho, p, pco) the step leaves rho, p, pco at their first-stage values.  The evaluation the
+    reference runs before its integrator (particles.py:478: "Is this derivative step required?") is not repeated:
+    the integrator's first stage recomputes the same derivatives from the same state."""
+
+    def __init__(self, sim, box_kind="periodic", thermostat_temp=None, eos=(2.0, 0.5, 1.0)):
+        if box_kind not in ("periodic", "mirror", "none"):
+            raise ValueError("box_kind is 'periodic', 'mirror' or 'none'")
+        self.sim, self.box_kind, self.thermostat_temp, self.eos = sim, box_kind, thermostat_temp, eos
+        self.steps = 0
+
+    def _migrate_with(self, extra):
+        """Re-home the owned particles together with per-particle columns `extra` (n_owned, C)."""
+        sim = self.sim
+        rows = torch.cat([sim.rows(), extra], dim=1)
+        rows = sim.dec.migrate(rows)
+        sim._load_rows(rows[:, :NCOL])
+        return rows[:, NCOL:]
+
+    def step(self, dt):
+        sim = self.sim
+        sim.evaluate()                                                     # stage 1
+        n, S = sim.n_owned, sim.S
+        # start state, first-stage derivatives and the fields the step leaves at their first-stage values
+        cols = [S["r"][:n], S["v"][:n], S["u"][:n, None], S["vdot"][:n], S["udot"][:n, None],
+                S["rho"][:n, None], S["p"][:n, None], S["pco"][:n, None]]
+        carry = torch.cat([c.reshape(n, -1) for c in cols], dim=1).clone()
+        R0, V0, U0, VD0, UD0, RHO, P, PCO = 0, 3, 6, 7, 10, 11, 12, 13
+        # predictor: x = x_start + xdot * dt   (integrator.py:52-53)
+        S["r"][:n] = carry[:, R0:R0 + 3] + carry[:, V0:V0 + 3] * dt
+        S["v"][:n] = carry[:, V0:V0 + 3] + carry[:, VD0:VD0 + 3] * dt
+        carry = self._migrate_with(carry)
+        sim.evaluate()                                                     # stage 2 at the predicted state
+        n, S = sim.n_owned, sim.S
+        v1 = S["v"][:n].clone()
+        # corrector: x = x_start + (c1 + c2) / 2   (integrator.py:56-59)
+        S["r"][:n] = carry[:, R0:R0 + 3] + (carry[:, V0:V0 + 3] + v1) * (0.5 * dt)
+        S["v"][:n] = carry[:, V0:V0 + 3] + (carry[:, VD0:VD0 + 3] + S["vdot"][:n]) * (0.5 * dt)
+        S["u"][:n] = carry[:, U0] + (carry[:, UD0] + S["udot"][:n]) * (0.5 * dt)
+        S["rho"][:n], S["p"][:n], S["pco"][:n] = carry[:, RHO], carry[:, P], carry[:, PCO]
+        self._box_apply(S["r"][:n], S["v"][:n])
+        if self.thermostat_temp is not None:
+            self._thermostat(S, n)
+        # final positions decide the owner for the next step; u, rho, p, pco go along
+        keep = torch.stack([S["u"][:n], S["rho"][:n], S["p"][:n], S["pco"][:n]], dim=1)
+        keep = self._migrate_with(keep)
+        n, S = sim.n_owned, sim.S
+        S["u"][:n], S["rho"][:n], S["p"][:n], S["pco"][:n] = keep[:, 0], keep[:, 1], keep[:, 2], keep[:, 3]
+        self.steps += 1
+
+    def _box_apply(self, r, v):
+        box = self.sim.dec.box
+        for d in range(3):
+            x = r[:, d]
+            if self.box_kind == "periodic":                # box.py:35-47: reset to the opposite face, not wrapped
+                hi, lo = x > box[d], x < 0
+                x[hi] = 0.0
+                x[lo] = box[d]
+            elif self.box_kind == "mirror":                # box.py:53-73
+                hi, lo = x > box[d], x < 0
+                x[hi] = box[d]
+                x[lo] = 0.0
+                v[:, d][hi | lo] *= -1.0
+
+    def _thermostat(self, S, n):
+        """particles.py:450-457 with the mean taken over all ranks."""
+        acc = torch.stack([S["t"][:n].sum(), torch.tensor(float(n), dtype=torch.float64, device=S["t"].device)])
+        if self.sim.dec.world > 1:
+            dist.all_reduce(acc, group=self.sim.dec.group)
+        tav = acc[0] / acc[1]
+        S["t"][:n] *= self.thermostat_temp / tav
+        a, _, kb = self.eos
+        S["u"][:n] = S["t"][:n] * kb - a * S["rho"][:n]                   # eos.get_vdw_u = vdw_energy (properties.py:46)
+
+
 def make_rows(r, v, m, h, t, gid):
     n = r.shape[0]
     rows = torch.empty((n, NCOL), dtype=torch.float64, device=r.device)
