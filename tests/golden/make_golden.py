@@ -200,7 +200,61 @@ def conduction():
     print("conduction_729         max|udot|=%.4e" % np.abs(p.udot).max())
 
 
+def force_variants():
+    """The reference's other pressure-force classes on one seeded system: forces.CohesiveSpamForce (forces.py:371-405),
+    forces.SpamForce2d (:246-274), forces.CohesiveSpamForce2d (:277-318, which as shipped applies the repulsive
+    pressure) and the accumulation of two forces into the same vdot / udot.  The long-range inputs the cohesive
+    force reads (p.rho_lr, nl.dwij_lr) are only ever filled by the reference's Fortran path; here they are set from
+    the reference's own lucy_kernel with the long smoothing length, per pair, in list order, and saved with the
+    outputs, so the fixture pins the force arithmetic for given inputs."""
+    r, v = lattice(7, 7, 7, seed=20270, jitter=0.3)
+    n = r.shape[0]
+    rng = np.random.default_rng(20271)
+    m, t = rng.uniform(0.8, 1.2, n), rng.uniform(0.8, 1.2, n)
+    box = (7.0, 7.0, 7.0)
+    hs, hl = 2.0, 3.0
+    p = particles.SmoothParticleSystem(n, d=3, maxn=n, xmax=box[0], ymax=box[1], zmax=box[2])
+    p.r[:, :] = r
+    p.v[:, :] = v
+    p.m[:] = m
+    p.h[:] = hs
+    p.hlr[:] = hl
+    p.t[:] = t
+    nl = neighbour_list.VerletList(p, cutoff=3.0, tolerance=0.0)
+    nl.build()
+    k = nl.nip
+    neighbour_list.NeighbourList.separations(nl)
+    properties.spam_properties(p, nl)
+    p.rho_lr[:] = spkernel.lucy_kernel(0.0, np.zeros(3), hl)[0]
+    for q in range(k):
+        i, j = nl.iap[q]
+        w, dw = spkernel.lucy_kernel(nl.rij[q], nl.drij[q], hl)
+        nl.wij_lr[q] = w
+        nl.dwij_lr[q, :] = dw
+        p.rho_lr[i] += w * p.m[j]
+        p.rho_lr[j] += w * p.m[i]
+    out = dict(r=r, v=v, m=m, t_in=t, box=np.array(box), hs=hs, hl=hl, cutoff=3.0, tolerance=0.0,
+               iap=nl.iap[:k].astype(np.int32), rij=nl.rij[:k].copy(), dv=nl.dv[:k].copy(), dwij=nl.dwij[:k].copy(),
+               dwij_lr=nl.dwij_lr[:k].copy(), rho=p.rho.copy(), rho_lr=p.rho_lr.copy(), p=p.p.copy(), pco=p.pco.copy())
+    for name, cls, cut in (("cohesive", forces.CohesiveSpamForce, 10.0), ("spam2d", forces.SpamForce2d, 5.0),
+                           ("cohesive2d", forces.CohesiveSpamForce2d, 10.0), ("cohesive_short", forces.CohesiveSpamForce, 2.5)):
+        p.vdot[:, :] = 0.0
+        p.udot[:] = 0.0
+        cls(p, nl, cutoff=cut).apply()
+        out["vdot_" + name], out["udot_" + name], out["fcut_" + name] = p.vdot.copy(), p.udot.copy(), cut
+    p.vdot[:, :] = 0.0
+    p.udot[:] = 0.0
+    forces.SpamForce(p, nl, cutoff=5.0).apply()
+    forces.CohesiveSpamForce(p, nl, cutoff=10.0).apply()
+    out["vdot_stacked"], out["udot_stacked"] = p.vdot.copy(), p.udot.copy()
+    np.savez_compressed(os.path.join(HERE, "force_variants_343.npz"), **out)
+    print("force_variants_343     pairs=%d  max|vdot| cohesive %.4e  2d %.4e" %
+          (k, np.abs(out["vdot_cohesive"]).max(), np.abs(out["vdot_spam2d"]).max()))
+
+
 if __name__ == "__main__":
-    main()
-    c1_trajectory()
-    conduction()
+    if "--only-force-variants" not in sys.argv:
+        main()
+        c1_trajectory()
+        conduction()
+    force_variants()

@@ -160,3 +160,37 @@ def test_builder_defined_viscous_statement_invariants():
     assert np.abs(vd.sum(axis=0)).max() < 1e-13 * np.abs(vd).sum()
     assert ud.sum() > 0.0 and (vd[:, 0] * vs[:, 0]).sum() < 0.0
     assert abs(ud.sum() + (vd * vs).sum()) < 1e-12 * abs(ud.sum())               # kinetic energy lost = heat gained
+
+
+@pytest.mark.parametrize("impl", ["numpy", "c"])
+def test_force_variants_match_reference(golden_dir, impl):
+    """forces.CohesiveSpamForce, SpamForce2d, CohesiveSpamForce2d and two forces stacked, as the reference
+    computes them (tests/golden/make_golden.py:force_variants); the long-range inputs come from the fixture."""
+    g = np.load(os.path.join(golden_dir, "force_variants_343.npz"))
+    n = g["r"].shape[0]
+    iap = g["iap"].astype(np.int64)
+    m, rij, dv = g["m"], g["rij"], g["dv"]
+    F = (lambda *a, **k: O.spam_force(*a, **k)) if impl == "numpy" else \
+        (lambda n_, m_, pr, rho, ia, rij_, dw, dv_, cutoff=5.0, dim=3, vdot=None, udot=None:
+         C.force(n_, m_, pr, rho, ia, rij_, dw, dv_, cutoff, dim, vdot, udot))
+    # long-range density and kernel gradient restated from the pair list (the oracle's Lucy kernel with h = hl)
+    hl = float(g["hl"])
+    w_lr, dw_lr = O.lucy_kernel_pairs(rij, g["drij"] if "drij" in g.files else _drij(g), np.full(iap.shape[0], hl))
+    rho_lr = np.full(n, O.lucy_kernel(0.0, (0., 0., 0.), hl)[0])
+    O._scatter_pairs(rho_lr, iap, w_lr * m[iap[:, 1]], w_lr * m[iap[:, 0]])
+    assert _close(dw_lr, g["dwij_lr"]) and _close(rho_lr, g["rho_lr"])
+    cases = [("cohesive", g["pco"], g["rho_lr"], g["dwij_lr"], 3), ("spam2d", g["p"], g["rho"], g["dwij"], 2),
+             ("cohesive2d", g["p"], g["rho"], g["dwij"], 2), ("cohesive_short", g["pco"], g["rho_lr"], g["dwij_lr"], 3)]
+    for name, press, rho, dw, dim in cases:
+        vd, ud = F(n, m, press, rho, iap, rij, dw, dv, cutoff=float(g["fcut_" + name]), dim=dim)
+        assert _close(vd, g["vdot_" + name]) and _close(ud, g["udot_" + name]), name
+    assert np.any(g["vdot_cohesive_short"] != g["vdot_cohesive"])       # the force's own cutoff does filter pairs
+    vd, ud = F(n, m, g["p"], g["rho"], iap, rij, g["dwij"], dv, cutoff=5.0)
+    vd, ud = F(n, m, g["pco"], g["rho_lr"], iap, rij, g["dwij_lr"], dv, cutoff=10.0, vdot=vd, udot=ud)
+    assert _close(vd, g["vdot_stacked"]) and _close(ud, g["udot_stacked"])
+
+
+def _drij(g):
+    """Pair separations of the fixture's list (the fixture keeps rij only)."""
+    box = tuple(float(x) for x in g["box"])
+    return O.separations(g["iap"].astype(np.int64), g["r"], g["v"], box)[0]
