@@ -252,9 +252,42 @@ def force_variants():
           (k, np.abs(out["vdot_cohesive"]).max(), np.abs(out["vdot_spam2d"]).max()))
 
 
+def integrator_state0():
+    return np.array([[0.3, -1.2, 0.8, 2.0], [0.0, 0.5, -0.7, 0.1], [1.0, 1.5, 0.25, -0.4]])
+
+
+def integrator_rhs(x):
+    """A small nonlinear system (three coupled rows) for the stepper fixture."""
+    return np.stack([x[1], -np.sin(x[0]) - 0.1 * x[1] * x[2], 0.5 * x[0] * x[1] - 0.2 * x[2]])
+
+
+def integrators():
+    """integrator.euler / imp_euler / rk4 (integrator.py:14-103) driven through their callback protocol."""
+    import integrator
+    out = {"x0": integrator_state0(), "dt": 0.05, "steps": 6}
+    for name in ("euler", "imp_euler", "rk4"):
+        box = {"x": integrator_state0(), "xdot": None}
+
+        def calc():
+            box["xdot"] = integrator_rhs(box["x"])
+
+        def setx(x):
+            box["x"] = x.copy()
+
+        for _ in range(out["steps"]):
+            getattr(integrator, name)(lambda: box["x"], calc, lambda: box["xdot"], setx, out["dt"])
+        out[name] = box["x"].copy()
+    np.savez_compressed(os.path.join(HERE, "integrators.npz"), **out)
+    print("integrators            euler %.6f  imp_euler %.6f  rk4 %.6f" % tuple(out[k][0, 0] for k in ("euler", "imp_euler", "rk4")))
+
+
 if __name__ == "__main__":
+    if "--only-integrators" in sys.argv:
+        integrators()
+        sys.exit(0)
     if "--only-force-variants" not in sys.argv:
         main()
         c1_trajectory()
         conduction()
+        integrators()
     force_variants()
