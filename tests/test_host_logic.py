@@ -27,3 +27,34 @@ def test_steppers_match_reference(golden_dir, name):
     for _ in range(int(g["steps"])):
         getattr(integrator, name)(lambda: box["x"], calc, lambda: box["xdot"], setx, float(g["dt"]))
     assert np.array_equal(box["x"].numpy(), g[name])
+
+
+def test_scalar_kernel_and_eos_known_answers(golden_dir):
+    """spkernel.lucy_kernel (spkernel.py:86-118) and properties.vdw / vdw_energy / vdw_temp (properties.py:38-49)
+    of the product's host API against the reference's answers (tests/golden/kat.npz) and SURVEY.md section 8c."""
+    from pyticles_b200 import properties, spkernel
+    k = np.load(os.path.join(golden_dir, "kat.npz"))
+    seen = 0
+    for name in k.files:
+        if not name.startswith("lucy_"):
+            continue
+        r, h, dim, dx0, dx1, dx2, w, g0, g1, g2 = k[name]
+        dx = (dx0, dx1, dx2)[:int(dim)]
+        pw, pg = spkernel.lucy_kernel(r, dx, h)
+        assert pw == pytest.approx(w, rel=1e-14, abs=1e-300)
+        pg = [pg] * int(dim) if not isinstance(pg, (list, tuple)) else pg       # r == 0: the reference returns a scalar 0
+        assert np.allclose(pg, (g0, g1, g2)[:int(dim)], rtol=1e-14, atol=1e-300)
+        seen += 1
+    assert seen >= 5
+    assert spkernel.lucy_kernel(0.0, (0., 0., 0.), 2.0)[0] == pytest.approx(0.2611135785101408, rel=1e-15)
+    assert spkernel.lucy_kernel(2.5, (2.5, 0., 0.), 2.0) == (0, [0, 0, 0])
+    assert spkernel.kernel(1.0, (1., 0., 0.), 2.0, 'lucy')[0] == pytest.approx(0.081597993284419, rel=1e-15)
+    with pytest.raises(NotImplementedError):
+        spkernel.kernel(1.0, (1., 0., 0.), 2.0, 'gaussian')
+    t = lambda x: torch.tensor(x, dtype=torch.float64)
+    p, pco = properties.vdw(t(1.0), t(1.0))
+    assert (float(p), float(pco)) == tuple(k["vdw_1_1"]) == (2.0, -2.0)
+    p, pco = properties.vdw(t(0.5), t(1.5))
+    assert (float(p), float(pco)) == tuple(k["vdw_05_15"])
+    assert float(properties.vdw_energy(t(1.0), t(5.0))) == float(k["vdw_energy_1_5"]) == 3.0
+    assert float(properties.vdw_temp(t(1.0), t(3.0))) == float(k["vdw_temp_1_3"]) == 5.0
