@@ -58,3 +58,19 @@ def test_scalar_kernel_and_eos_known_answers(golden_dir):
     assert (float(p), float(pco)) == tuple(k["vdw_05_15"])
     assert float(properties.vdw_energy(t(1.0), t(5.0))) == float(k["vdw_energy_1_5"]) == 3.0
     assert float(properties.vdw_temp(t(1.0), t(3.0))) == float(k["vdw_temp_1_3"]) == 5.0
+
+
+def test_host_minimum_image_rows():
+    """neighbour_list.py:105-123 on rows: one shift, strict comparisons against L/2 -- including values exactly on
+    +-L/2 (not shifted) and beyond 3L/2 (shifted once only)."""
+    from oracle import oracle as O
+    from pyticles_b200.neighbour_list import _minimum_image_rows
+    L = (10.0, 6.0, 7.5)
+    rng = np.random.default_rng(3)
+    d = rng.uniform(-2.0, 2.0, size=(500, 3)) * np.array(L)
+    d[:6] = [[5.0, 3.0, 3.75], [-5.0, -3.0, -3.75], [5.000000000000001, -3.0000000000000004, 3.7500000000000004],
+             [16.0, -10.0, 12.0], [0.0, 0.0, 0.0], [-15.1, 9.1, -11.3]]
+    got = _minimum_image_rows(torch.from_numpy(d), *L).numpy()
+    assert np.array_equal(got, O.minimum_image(d, *L))
+    assert np.array_equal(got[0], d[0]) and np.array_equal(got[1], d[1])          # exactly on the boundary: kept
+    assert np.array_equal(got[3], [6.0, -4.0, 4.5])                                # one shift only
