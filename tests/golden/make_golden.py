@@ -281,7 +281,44 @@ def integrators():
     print("integrators            euler %.6f  imp_euler %.6f  rk4 %.6f" % tuple(out[k][0, 0] for k in ("euler", "imp_euler", "rk4")))
 
 
+PS_ARGS = dict(n=27, d=3, maxn=40, xmax=6.0, ymax=5.0, zmax=4.0, vmax=0.0, mass=0.1386, temperature=0.8,
+               thermostat_temp=0.9, thermostat=True, hshort=1.5, hlong=3.0, integrator='rk4')
+
+
+def particle_system():
+    """SmoothParticleSystem storage (particles.py:69-169,256-359): the defaults its constructor leaves in the
+    per-particle arrays, and the [11, maxn] state / derivative mappings (particles.py:496-542)."""
+    kw = dict(PS_ARGS)
+    n = kw.pop("n")
+    p = particles.SmoothParticleSystem(n, **kw)
+    out = {"defaults_" + k: getattr(p, k).copy() for k in ("m", "v", "t", "u", "h", "hlr", "rho", "p", "pco", "udot", "vdot")}
+    out["step_name"] = p.step.__name__
+    out["box_type"] = type(p.box).__name__
+    out["timing_keys"] = np.array(sorted(p.timing))
+    rng = np.random.default_rng(20272)
+    fields = {}
+    for k in ("r", "v", "rdot", "vdot"):
+        fields[k] = rng.normal(size=(p.maxn, 3))
+    for k in ("m", "mdot", "rho", "rhodot", "p", "pco", "u", "udot"):
+        fields[k] = rng.normal(size=p.maxn)
+    for k, a in fields.items():
+        getattr(p, k)[...] = a
+        out["in_" + k] = a
+    out["x"] = p.gather_state().copy()
+    out["xdot"] = p.gather_derivatives().copy()
+    x2 = rng.normal(size=p.x.shape)
+    out["x2"] = x2
+    p.scatter_state(x2)
+    for k in ("m", "r", "v", "rho", "p", "pco", "u"):
+        out["scattered_" + k] = getattr(p, k).copy()
+    np.savez_compressed(os.path.join(HERE, "particle_system.npz"), **out)
+    print("particle_system        x %s  step %s  box %s" % (out["x"].shape, out["step_name"], out["box_type"]))
+
+
 if __name__ == "__main__":
+    if "--only-particle-system" in sys.argv:
+        particle_system()
+        sys.exit(0)
     if "--only-integrators" in sys.argv:
         integrators()
         sys.exit(0)
@@ -290,4 +327,5 @@ if __name__ == "__main__":
         c1_trajectory()
         conduction()
         integrators()
+        particle_system()
     force_variants()

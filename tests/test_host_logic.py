@@ -74,3 +74,26 @@ def test_host_minimum_image_rows():
     assert np.array_equal(got, O.minimum_image(d, *L))
     assert np.array_equal(got[0], d[0]) and np.array_equal(got[1], d[1])          # exactly on the boundary: kept
     assert np.array_equal(got[3], [6.0, -4.0, 4.5])                                # one shift only
+
+
+def test_particle_system_storage_matches_reference(golden_dir):
+    """SmoothParticleSystem on CPU tensors: constructor defaults, integrator / box choice, timing keys and the
+    [11, maxn] state and derivative mappings (particles.py:69-169,256-359,496-542) against the reference's
+    (tests/golden/particle_system.npz)."""
+    from pyticles_b200 import particles
+    g = np.load(os.path.join(golden_dir, "particle_system.npz"))
+    p = particles.SmoothParticleSystem(27, d=3, maxn=40, xmax=6.0, ymax=5.0, zmax=4.0, vmax=0.0, mass=0.1386,
+                                       temperature=0.8, thermostat_temp=0.9, thermostat=True, hshort=1.5, hlong=3.0,
+                                       integrator='rk4', device="cpu")
+    for k in ("m", "v", "t", "u", "h", "hlr", "rho", "p", "pco", "udot", "vdot"):
+        assert np.array_equal(getattr(p, k).numpy(), g["defaults_" + k]), k
+    assert p.step.__name__ == str(g["step_name"]) and type(p.box).__name__ == str(g["box_type"])
+    assert set(g["timing_keys"].tolist()) <= set(p.timing)
+    assert p.thermostat is True and p.thermostat_temp == 0.9 and (p.n, p.maxn, p.dim) == (27, 40, 3)
+    for k in ("r", "v", "rdot", "vdot", "m", "mdot", "rho", "rhodot", "p", "pco", "u", "udot"):
+        getattr(p, k)[...] = torch.from_numpy(g["in_" + k])
+    assert np.array_equal(p.gather_state().numpy(), g["x"])
+    assert np.array_equal(p.gather_derivatives().numpy(), g["xdot"])
+    p.scatter_state(torch.from_numpy(g["x2"]))
+    for k in ("m", "r", "v", "rho", "p", "pco", "u"):
+        assert np.array_equal(getattr(p, k).numpy(), g["scattered_" + k]), k
