@@ -459,9 +459,16 @@ class SlabStepper(object):
         sim._load_rows(rows[:, :NCOL])
         return rows[:, NCOL:]
 
+    def _evaluate(self):
+        """One derivative evaluation, settled: a neighbour-capacity overflow is grown and re-evaluated (check())
+        before its truncated sums can enter the step."""
+        self.sim.evaluate()
+        if hasattr(self.sim, "check"):
+            self.sim.check()
+
     def step(self, dt):
         sim = self.sim
-        sim.evaluate()                                                     # stage 1
+        self._evaluate()                                                   # stage 1
         n, S = sim.n_owned, sim.S
         # start state, first-stage derivatives and the fields the step leaves at their first-stage values
         cols = [S["r"][:n], S["v"][:n], S["u"][:n, None], S["vdot"][:n], S["udot"][:n, None],
@@ -472,7 +479,7 @@ class SlabStepper(object):
         S["r"][:n] = carry[:, R0:R0 + 3] + carry[:, V0:V0 + 3] * dt
         S["v"][:n] = carry[:, V0:V0 + 3] + carry[:, VD0:VD0 + 3] * dt
         carry = self._migrate_with(carry)
-        sim.evaluate()                                                     # stage 2 at the predicted state
+        self._evaluate()                                                   # stage 2 at the predicted state
         n, S = sim.n_owned, sim.S
         v1 = S["v"][:n].clone()
         # corrector: x = x_start + (c1 + c2) / 2   (integrator.py:56-59)
