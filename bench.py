@@ -206,6 +206,92 @@ def cpu_baseline():
                       "+ force) of oracle/sph_oracle.c" % (side[0], side[1], side[2], n, reps)}
 
 
+# ------------------------------------------------------------------ parity gate (the oracle as the checker)
+def parity_gate(sim, wl, world, rank, device):
+    """Before any timing is reported: one evaluation of the benched system is compared with the CPU oracle
+    (oracle/sph_oracle.c) on a sub-box -- a core of up to 48^3 lattice cells plus a margin of two cutoffs, so that
+    every core particle and every neighbour of it has its complete neighbourhood inside the sample; with more than
+    one GPU the core straddles the slab face between rank 0 and rank 1.  Core particles: neighbour SETS bit-exact,
+    rho / p / vdot / udot within 1e-10 (normalised as in the tests).  Returns the `parity` block of the JSON line."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    nx, ny, nz = wl["dims"]
+    nxl = nx // world if wl["scaling"] == "strong" else nx
+    dims = (nxl * world, ny, nz)
+    pad = 2.0 * CUTOFF + 0.5
+    centre = [float(nxl) if world > 1 else dims[0] / 2.0, dims[1] / 2.0, dims[2] / 2.0]
+    half = []
+    for d in range(3):
+        room = (nxl if (d == 0 and world > 1) else dims[d] / 2.0) - pad - 0.5
+        half.append(min(24.0, room) if dims[d] > 1 else None)        # None: a sheet, every z belongs to the core
+    if any(h is not None and h < 2.0 for h in half):
+        return {"checked": 0, "skipped": "box too small for a sub-box with a margin of two cutoffs"}
+    st = sim.owned_state()
+    t_in = st["t"].clone()
+    sim.evaluate()
+    sim.check()
+    res = sim.owned_results()
+    r = st["r"]
+    in_core = torch.ones(r.shape[0], dtype=torch.bool, device=device)
+    in_samp = torch.ones(r.shape[0], dtype=torch.bool, device=device)
+    for d in range(3):
+        if half[d] is None:
+            continue
+        in_core &= (r[:, d] >= centre[d] - half[d]) & (r[:, d] < centre[d] + half[d])
+        in_samp &= (r[:, d] >= centre[d] - half[d] - pad) & (r[:, d] < centre[d] + half[d] + pad)
+    idx = torch.nonzero(in_samp).flatten()
+    core_idx = torch.nonzero(in_core).flatten()
+    mine = {k: st[k][idx].cpu().numpy() for k in ("r", "v", "gid")}
+    mine["t"] = t_in[idx].cpu().numpy()
+    mine["core"] = in_core[idx].cpu().numpy()
+    for k in ("rho", "p", "vdot", "udot"):
+        mine[k] = res[k][idx].cpu().numpy()
+    mine["rows"] = sim.neighbour_gids(core_idx).cpu().numpy()
+    mine["rows_gid"] = st["gid"][core_idx].cpu().numpy()
+    parts = [mine]
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+    if rank != 0:
+        return None
+    from oracle import c_oracle as C
+    cat = {k: np.concatenate([x[k] for x in parts]) for k in mine if k != "rows"}
+    width = max(x["rows"].shape[1] for x in parts)
+    rows = np.concatenate([np.pad(x["rows"], ((0, 0), (0, width - x["rows"].shape[1])), constant_values=-1)
+                           for x in parts])
+    order = np.argsort(cat["gid"], kind="stable")
+    gid = cat["gid"][order]
+    n = gid.shape[0]
+    box = np.array([float(dims[0]), float(dims[1]), float(wl["zbox"] or dims[2])])
+    ref = C.sph_step(np.ascontiguousarray(cat["r"][order]), np.ascontiguousarray(cat["v"][order]), np.ones(n),
+                     np.full(n, H), np.ascontiguousarray(cat["t"][order]), box, CUTOFF, TOL, FCUT, *EOS)
+    core = cat["core"][order]
+    # neighbour sets of the core particles, as sorted global ids
+    iap = ref["iap"].astype(np.int64)
+    both = np.concatenate([iap, iap[:, ::-1]])
+    both = both[core[both[:, 0]]]
+    both = both[np.lexsort((gid[both[:, 1]], both[:, 0]))]
+    want_cnt = np.bincount(both[:, 0], minlength=n)[core]
+    ro = np.argsort(cat["rows_gid"], kind="stable")
+    got = np.sort(np.where(rows[ro] < 0, np.iinfo(np.int64).max, rows[ro]), axis=1)
+    got_cnt = (rows[ro] >= 0).sum(axis=1)
+    sets_ok = bool(np.array_equal(cat["rows_gid"][ro], gid[core]) and np.array_equal(got_cnt, want_cnt) and
+                   np.array_equal(got[got < np.iinfo(np.int64).max], gid[both[:, 1]]))
+    errs = {}
+    for k in ("rho", "p", "vdot", "udot"):
+        a, b = cat[k][order][core], ref[k][core]
+        scale = np.maximum(np.abs(b), 1e-3 * np.max(np.abs(b)))
+        errs[k] = float(np.max(np.abs(a - b) / scale))
+    out = {"checked": int(core.sum()), "sample": int(n), "pairs_checked": int(both.shape[0] // 2),
+           "neighbour_sets_equal": sets_ok, "max_rel": max(errs.values()), "rel": errs, "tol": 1e-10,
+           "oracle": "oracle/sph_oracle.c on a %s sub-box%s" % (
+               "x".join("%d" % (2 * h) if h is not None else "all" for h in half),
+               " straddling the rank 0 / rank 1 slab face" if world > 1 else ""),
+           "ok": bool(sets_ok and max(errs.values()) < 1e-10)}
+    return out
+
+
 # ------------------------------------------------------------------ our arm
 _REAL_STDOUT = None
 
@@ -236,6 +322,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle parity gate (on by default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -263,6 +350,11 @@ def main():
         sim.evaluate()
     sim.check()
     torch.cuda.synchronize()
+    parity = None
+    if not args.no_check:
+        parity = parity_gate(sim, wl, world, rank, device)
+        if rank == 0 and not parity.get("ok", True):
+            sys.stderr.write("PARITY GATE FAILED: %s\n" % json.dumps(parity))
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -342,12 +434,16 @@ def main():
                       "max_nbrs": sim.max_nbrs},
            "roofline": roof, "gpu_launches": sim.launches_per_eval * args.steps}
     out["config"]["tile_fallback"] = tile_fallback
+    if parity is not None:
+        out["parity"] = parity
     if clocks:
         out["clocks"] = clocks
     if e2e:
         out["e2e"] = {"value": n_total * e2e["steps"] / (e2e["ms"] * 1e-3), "unit": UNIT,
                       "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
-                      "ms_per_step": e2e["ms"] / e2e["steps"]}
+                      "static_bytes": e2e["static"], "ms_per_step": e2e["ms"] / e2e["steps"],
+                      "note": "r, v, t in and rho, p, vdot, udot out every step; m and h (constant between the "
+                              "evaluations of a run) uploaded once = static_bytes"}
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     emit(out)

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SPH_ABI_VERSION 1
+#define SPH_ABI_VERSION 3      /* sph_version() reports the same number */
 
 enum {
     SPH_OK = 0,
@@ -49,20 +49,22 @@ enum {
     SPH_F_NBR_OVERFLOW = 8,   /* some particle has more neighbours than `max_nbrs`;
                                  sph_status.max_count says how many are needed */
     SPH_F_OUT_OF_SLAB = 16,   /* a particle lies outside the local cell-layer range */
-    SPH_F_TILE_FALLBACK = 32  /* the cell-group (tile) neighbour kernel met a case outside its
+    SPH_F_TILE_FALLBACK = 32, /* the cell-group (tile) neighbour kernel met a case outside its
                                  fixed capacities (a cell with > 64 particles, > 1280 particles
                                  in the 64 cells around a group, > 32 hits in one stream's list,
                                  positions far outside the box): the general kernel did the
                                  pass.  The neighbour structure is the same either way (rows
                                  hold the same sets); only speed differs. */
+    SPH_F_HALO_OVERFLOW = 64  /* a boundary cell layer holds more particles than the halo buffers
+                                 (sph_status.halo_count says how many): the ghosts are incomplete */
 };
 
 /* Device-resident status block (64 bytes).  Zero it with sph_status_reset before a build. */
 typedef struct sph_status {
     uint32_t flags;
     uint32_t max_count;          /* largest per-particle neighbour count seen */
-    unsigned long long n_links;  /* sum of per-particle neighbour counts = 2 * nip */
-    unsigned long long n_exact;  /* candidates that needed the fp64 predicate */
+    uint32_t halo_count[2];      /* particles in the left / right boundary cell layer (sph_cells_begin) */
+    uint32_t ghost_count[2];     /* ghosts received from the left / right neighbour (sph_halo_unpack) */
     unsigned long long dsq_max_bits; /* ponder_rebuild: max |r_old - r|^2 as ordered bits */
     uint32_t rebuild;            /* ponder_rebuild result (neighbour_list.py:225-234) */
     uint32_t reserved[7];
@@ -102,9 +104,9 @@ typedef struct sph_buffers {
     int32_t n;              /* particles */
     int32_t max_nbrs;       /* ELL capacity per particle (multiple of 4) */
     /* cell list */
-    uint32_t *cell_count;   /* [ncode]      */
-    uint32_t *cell_start;   /* [ncode + 1]  */
-    uint32_t *scan_tmp;     /* [sph_scan_tmp_elems(ncode)] */
+    uint32_t *cell_count;   /* [ncode + 1]  (the last cell collects the unused ghost slots, see n_valid) */
+    uint32_t *cell_start;   /* [ncode + 2]  */
+    uint32_t *scan_tmp;     /* [sph_scan_tmp_elems(ncode + 1)] */
     uint32_t *code;         /* [n] cell code of particle i (original order) */
     uint32_t *rank;         /* [n] arrival rank inside its cell */
     int32_t *perm;          /* [n] sorted position -> original index */
@@ -116,6 +118,16 @@ typedef struct sph_buffers {
     int32_t *nbr;           /* [ceil(n/32)*32 * max_nbrs] warp-transposed ELL rows */
     int32_t *cnt;           /* [n] neighbours per sorted particle */
     sph_status *status;     /* [1] */
+    /* multi-GPU slab decomposition (all zero / NULL on one GPU) */
+    const int32_t *n_valid; /* device scalar or NULL: particle slots >= *n_valid hold no particle (the ghost
+                               region has a fixed capacity so that no count has to travel to the host); they
+                               are binned into a spare cell behind the table that no pass visits */
+    const int64_t *sort_key;/* [n] or NULL: ghosts (original index >= n_owned) are ordered by this key (their
+                               global id) inside a cell instead of by their arrival slot, so results do not
+                               depend on the order in which the neighbour rank packed them */
+    int32_t n_owned;        /* > 0: original indices >= n_owned are ghosts -- binned and listed as neighbours of
+                               owned particles, but no rows, densities or forces are computed FOR them */
+    int32_t reserved0;
 } sph_buffers;
 
 /* ------------------------------------------------------------------ host-side planning */
@@ -142,6 +154,21 @@ int sph_status_reset(sph_status *d_status, void *stream);
  * cell (ascending original index).  Fills code, rank, cell_count, cell_start, perm.
  * First half of VerletList.build (neighbour_list.py:160-189). */
 int sph_cells_build(const sph_grid *grid, const sph_buffers *buf, const double *d_r, void *stream);
+
+/* The same in three steps, for the slab decomposition: the owned particles are binned BEFORE the ghosts
+ * arrive, and that pass also lists the particles of the two boundary cell layers (local x layers 1 and
+ * ncl[0] - 2: sph_grid_restrict_x keeps one ghost layer on each side) -- the ghosts the x-neighbours need --
+ * at no extra pass over the positions.
+ *   begin   zeroes the cell counters and bins particles [first, first + count); d_idx_left / d_idx_right
+ *           (each `cap` entries, may be NULL) receive the boundary-layer indices in arrival order, their
+ *           numbers go to sph_status.halo_count (which may exceed cap: SPH_F_HALO_OVERFLOW at pack time)
+ *   add     bins a further range (the ghost slots; slots >= *buf->n_valid go to the spare cell)
+ *   finish  scan, scatter, canonical order inside the cells */
+int sph_cells_begin(const sph_grid *grid, const sph_buffers *buf, const double *d_r, int32_t first, int32_t count,
+                    int32_t *d_idx_left, int32_t *d_idx_right, int32_t cap, void *stream);
+int sph_cells_add(const sph_grid *grid, const sph_buffers *buf, const double *d_r, int32_t first, int32_t count,
+                  void *stream);
+int sph_cells_finish(const sph_grid *grid, const sph_buffers *buf, void *stream);
 
 /* Reorder particle state into the Morton-sorted working set (pos4, vel4, rel4) using
  * the existing perm.  Also what VerletList.separations amounts to when the list is kept
@@ -172,10 +199,12 @@ int sph_density_eos(const sph_grid *grid, const sph_buffers *buf, const sph_eos 
  * with the cohesive pressure it is CohesiveSpamForce (forces.py:371-405,
  * c_forces.pyx:131-182).  d_press and d_rho (original order) give press_i / rho_i^2; pass
  * both NULL to reuse the values the preceding sph_density_eos left in vel4[.,3].
- * ACCUMULATES into vdot[n,3], udot[n] (original order) as the reference does. */
+ * ACCUMULATES into vdot[n,3], udot[n] (original order) as the reference does; `first_force` != 0
+ * says vdot / udot would be all zero at this point (particles.py:549-550 zeroes them before the first
+ * force of an evaluation), so the results are stored instead and the caller need not zero them. */
 int sph_force(const sph_grid *grid, const sph_buffers *buf, const double *d_press,
               const double *d_rho, const double *d_h_orig, int h_uniform, int list_fresh,
-              double fcutoff, int dim, double *d_vdot, double *d_udot, void *stream);
+              double fcutoff, int dim, int first_force, double *d_vdot, double *d_udot, void *stream);
 
 /* Refresh press_i / rho_i^2 (the operand sph_force gathers) from original-order arrays for the
  * particles whose original index is >= first_orig only.  The slab decomposition uses it for the
@@ -244,34 +273,42 @@ int sph_ponder_rebuild(const double *d_r_old, const double *d_r, int32_t n, doub
 
 /* ------------------------------------------------------------------ multi-GPU slab decomposition */
 
-/* Indices of the particles whose global x cell layer (floor(x * inv_w) mod nc, the binning
- * formula of sph_cells_build) is layer_left / layer_right: the two boundary layers of a slab,
- * i.e. the ghosts its x-neighbours need.  x is read with a stride (in doubles).  d_counts[0..1]
- * receive the two counts (they may exceed `cap`, the capacity of each index list: only the
- * first cap indices are stored, so the caller retries with larger lists); index order inside
- * each list is unspecified (sort for determinism). */
-int sph_slab_select(const double *d_x, int64_t stride, int32_t n, double inv_w, int32_t nc,
-                    int32_t layer_left, int32_t layer_right, int32_t *d_idx_left, int32_t *d_idx_right,
-                    int32_t cap, uint32_t *d_counts, void *stream);
+/* Particle arrays of one rank in pyticles' layout (owned particles in front, ghost slots behind). */
+typedef struct sph_fields {
+    double *r, *v;          /* [n,3] */
+    double *m, *h, *t;      /* [n]   */
+    int64_t *gid;           /* [n] global particle id */
+} sph_fields;
 
-/* Halo rows of the slab decomposition: 10 doubles per boundary particle (r[3], v[3], m, h, t, global id as a
- * double).  pack gathers the particles d_idx[0..n_idx) into d_rows; unpack scatters received rows to the
- * particle slots first .. first + n_rows (the ghosts sit behind the owned particles).  pack2 / unpack2 do the
- * same for two per-particle scalars (p and rho, the second exchange of an evaluation). */
-int sph_halo_pack(const int64_t *d_idx, int64_t n_idx, const double *d_r, const double *d_v, const double *d_m,
-                  const double *d_h, const double *d_t, const int64_t *d_gid, double *d_rows, void *stream);
-int sph_halo_unpack(const double *d_rows, int64_t n_rows, int64_t first, double *d_r, double *d_v, double *d_m,
-                    double *d_h, double *d_t, int64_t *d_gid, void *stream);
-int sph_halo_pack2(const int64_t *d_idx, int64_t n_idx, const double *d_a, const double *d_b, double *d_out,
+#define SPH_HALO_COLS 10    /* doubles per halo row: r[3] v[3] m h t gid */
+
+/* Ghost exchange A of the slab decomposition with fixed-capacity buffers, so that no
+ * count ever travels to the host.  A send buffer is (cap + 1) rows of SPH_HALO_COLS doubles; row 0 is the
+ * header {rows that follow, particles in the layer, 0...}.
+ *   pack    rows of the boundary-layer particles d_idx_left / d_idx_right (from sph_cells_begin, counts in
+ *           status->halo_count) into d_send_left / d_send_right; more than cap: SPH_F_HALO_OVERFLOW
+ *   unpack  the buffers received from the left / right neighbour into the slots first, first + 1, ...
+ *           (left neighbour's particles, then the right's); writes the number of valid slots
+ *           first + ghosts to *d_n_valid and the two ghost counts to status->ghost_count */
+int sph_halo_pack(const sph_fields *f, const int32_t *d_idx_left, const int32_t *d_idx_right, int32_t cap,
+                  double *d_send_left, double *d_send_right, sph_status *d_status, void *stream);
+int sph_halo_unpack(const sph_fields *f, const double *d_recv_left, const double *d_recv_right, int32_t cap,
+                    int32_t first, int32_t *d_n_valid, sph_status *d_status, void *stream);
+/* Ghost exchange B: two per-particle scalars (p and rho) of the same particles in the same order; buffers
+ * are cap rows of 2 doubles, the counts are the ones exchange A left in the status block. */
+int sph_halo_pack2(const int32_t *d_idx_left, const int32_t *d_idx_right, int32_t cap, const double *d_a,
+                   const double *d_b, double *d_send_left, double *d_send_right, const sph_status *d_status,
                    void *stream);
-int sph_halo_unpack2(const double *d_in, int64_t n_rows, int64_t first, double *d_a, double *d_b, void *stream);
+int sph_halo_unpack2(const double *d_recv_left, const double *d_recv_right, int32_t cap, int32_t first,
+                     double *d_a, double *d_b, const sph_status *d_status, void *stream);
 
 /* ------------------------------------------------------------------ stepping helpers ("next" rows) */
 
 /* x <- a + s * b over len doubles: the state-vector updates of integrator.py:37-41,44-59,62-95. */
 int sph_axpy(double *d_x, const double *d_a, const double *d_b, double s, int64_t len, void *stream);
 
-/* box.MirrorBox.apply (box.py:51-73) / box.PeriodicBox.apply (box.py:33-47). kind: 0 mirror, 1 periodic */
+/* box.MirrorBox.apply (box.py:51-73) / box.PeriodicBox.apply (box.py:33-47). kind: 0 mirror, 1 periodic (the
+ * reference's reset to the opposite face), 2 true periodic wrap x - L floor(x / L) (not in the reference) */
 int sph_box_apply(const double box[3], int kind, double *d_r, double *d_v, int32_t n, void *stream);
 
 const char *sph_version(void);

@@ -17,6 +17,9 @@ SPH_F_OUT_OF_BOX = 4
 SPH_F_NBR_OVERFLOW = 8
 SPH_F_OUT_OF_SLAB = 16
 SPH_F_TILE_FALLBACK = 32
+SPH_F_HALO_OVERFLOW = 64
+SPH_ABI_VERSION = 3
+HALO_COLS = 10
 
 c_double3 = ctypes.c_double * 3
 c_int3 = ctypes.c_int32 * 3
@@ -26,8 +29,8 @@ c_uint3 = ctypes.c_uint32 * 3
 class SphStatus(ctypes.Structure):
     _fields_ = [("flags", ctypes.c_uint32),
                 ("max_count", ctypes.c_uint32),
-                ("n_links", ctypes.c_ulonglong),
-                ("n_exact", ctypes.c_ulonglong),
+                ("halo_count", ctypes.c_uint32 * 2),
+                ("ghost_count", ctypes.c_uint32 * 2),
                 ("dsq_max_bits", ctypes.c_ulonglong),
                 ("rebuild", ctypes.c_uint32),
                 ("reserved", ctypes.c_uint32 * 7)]
@@ -72,7 +75,16 @@ class SphBuffers(ctypes.Structure):
                 ("rel4", ctypes.c_void_p),
                 ("nbr", ctypes.c_void_p),
                 ("cnt", ctypes.c_void_p),
-                ("status", ctypes.c_void_p)]
+                ("status", ctypes.c_void_p),
+                ("n_valid", ctypes.c_void_p),
+                ("sort_key", ctypes.c_void_p),
+                ("n_owned", ctypes.c_int32),
+                ("reserved0", ctypes.c_int32)]
+
+
+class SphFields(ctypes.Structure):
+    _fields_ = [("r", ctypes.c_void_p), ("v", ctypes.c_void_p), ("m", ctypes.c_void_p), ("h", ctypes.c_void_p),
+                ("t", ctypes.c_void_p), ("gid", ctypes.c_void_p)]
 
 
 assert ctypes.sizeof(SphStatus) == 64
@@ -84,6 +96,7 @@ _dbl = ctypes.c_double
 _gp = ctypes.POINTER(SphGrid)
 _bp = ctypes.POINTER(SphBuffers)
 _ep = ctypes.POINTER(SphEos)
+_fp = ctypes.POINTER(SphFields)
 _d3 = ctypes.POINTER(ctypes.c_double)
 
 # name -> (restype, argtypes); every symbol include/pyticles_b200.h declares
@@ -95,12 +108,15 @@ SIGNATURES = {
     "sph_nbr_elems": (_i64, [_i32, _i32]),
     "sph_status_reset": (ctypes.c_int, [_vp, _vp]),
     "sph_cells_build": (ctypes.c_int, [_gp, _bp, _vp, _vp]),
+    "sph_cells_begin": (ctypes.c_int, [_gp, _bp, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "sph_cells_add": (ctypes.c_int, [_gp, _bp, _vp, _i32, _i32, _vp]),
+    "sph_cells_finish": (ctypes.c_int, [_gp, _bp, _vp]),
     "sph_gather": (ctypes.c_int, [_gp, _bp, _vp, _vp, _vp, _vp]),
     "sph_nlist_build": (ctypes.c_int, [_gp, _bp, _vp]),
     "sph_density_eos": (ctypes.c_int, [_gp, _bp, _ep, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        _vp, _vp, _vp, _vp, _vp, _vp]),
     "sph_force": (ctypes.c_int, [_gp, _bp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _dbl, ctypes.c_int,
-                                 _vp, _vp, _vp]),
+                                 ctypes.c_int, _vp, _vp, _vp]),
     "sph_pressure_term": (ctypes.c_int, [_bp, _vp, _vp, _i32, _vp]),
     "sph_conduction": (ctypes.c_int, [_gp, _bp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
     "sph_gradv": (ctypes.c_int, [_gp, _bp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
@@ -113,11 +129,10 @@ SIGNATURES = {
     "sph_pair_kernels": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sph_compress": (ctypes.c_int, [_gp, _bp, _vp]),
     "sph_ponder_rebuild": (ctypes.c_int, [_vp, _vp, _i32, _dbl, _vp, _vp]),
-    "sph_slab_select": (ctypes.c_int, [_vp, _i64, _i32, _dbl, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
-    "sph_halo_pack": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "sph_halo_unpack": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "sph_halo_pack2": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
-    "sph_halo_unpack2": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "sph_halo_pack": (ctypes.c_int, [_fp, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "sph_halo_unpack": (ctypes.c_int, [_fp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "sph_halo_pack2": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sph_halo_unpack2": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "sph_axpy": (ctypes.c_int, [_vp, _vp, _vp, _dbl, _i64, _vp]),
     "sph_box_apply": (ctypes.c_int, [_d3, ctypes.c_int, _vp, _vp, _i32, _vp]),
 }

@@ -96,9 +96,9 @@ class NeighbourBackend(object):
         ncode = int(g.ncode)
         b = self.buf
         b.n, b.max_nbrs = self.n, self.K
-        b.cell_count = _ptr(self._alloc("cell_count", ncode, torch.int32))
-        b.cell_start = _ptr(self._alloc("cell_start", ncode + 1, torch.int32))
-        b.scan_tmp = _ptr(self._alloc("scan_tmp", self.lib.sph_scan_tmp_elems(ncode), torch.int32))
+        b.cell_count = _ptr(self._alloc("cell_count", ncode + 1, torch.int32))
+        b.cell_start = _ptr(self._alloc("cell_start", ncode + 2, torch.int32))
+        b.scan_tmp = _ptr(self._alloc("scan_tmp", self.lib.sph_scan_tmp_elems(ncode + 1), torch.int32))
         b.code = _ptr(self._alloc("code", n, torch.int32))
         b.rank = _ptr(self._alloc("rank", n, torch.int32))
         b.perm = _ptr(self._alloc("perm", n, torch.int32))
@@ -165,7 +165,9 @@ class NeighbourBackend(object):
                                        _stream()), "sph_density_eos")
         self.press_ready = not long_range
 
-    def force(self, press, rho, h, h_uniform, fcutoff, dim, vdot, udot, reuse_press=False):
+    def force(self, press, rho, h, h_uniform, fcutoff, dim, vdot, udot, reuse_press=False, first_force=False):
+        """`first_force`: vdot / udot would be all zero here (the evaluation's first force): results are stored,
+        the caller need not zero them (particles.py:549-550)."""
         if reuse_press and self.press_ready:
             pp = rp = ctypes.c_void_p(0)
         else:
@@ -173,7 +175,8 @@ class NeighbourBackend(object):
             self.press_ready = False
         check(self.lib.sph_force(ctypes.byref(self.grid), ctypes.byref(self.buf), pp, rp, _ptr(_f64(h, "h")),
                                  int(bool(h_uniform)), int(self.fresh), float(fcutoff), int(dim),
-                                 _ptr(_f64(vdot, "vdot")), _ptr(_f64(udot, "udot")), _stream()), "sph_force")
+                                 int(bool(first_force)), _ptr(_f64(vdot, "vdot")), _ptr(_f64(udot, "udot")),
+                                 _stream()), "sph_force")
 
     def pressure_term(self, press, rho, first_orig):
         """vel4[., 3] = press/rho^2 for the particles with original index >= first_orig (ghosts)."""
@@ -231,6 +234,21 @@ class NeighbourBackend(object):
         iap = torch.empty((nip, 2), dtype=torch.int32, device=self.device)
         check(L.sph_pairs_fill(b, _ptr(row_start), _ptr(iap), nip, s), "sph_pairs_fill")
         return iap
+
+    def neighbour_rows(self, idx):
+        """Neighbour rows of the particles with ORIGINAL indices `idx` (int64 tensor [m]) as original indices,
+        [m, K] int64 padded with -1.  A diagnostic read-out of the ELL structure (bench.py's parity gate, tests);
+        not on the hot path."""
+        n, K = self.n, self.K
+        perm = self.t["perm"][:n].to(torch.int64)
+        inv = torch.empty(n, dtype=torch.int64, device=self.device)
+        inv[perm] = torch.arange(n, dtype=torch.int64, device=self.device)
+        a = inv[idx]
+        cnt = self.t["cnt"][:n].to(torch.int64)[a].clamp(max=K)
+        k = torch.arange(K, dtype=torch.int64, device=self.device)
+        off = ((a >> 5)[:, None] * K + k[None, :]) * 32 + (a & 31)[:, None]
+        rows = perm[self.t["nbr"][off.clamp(max=self.t["nbr"].numel() - 1)].to(torch.int64).clamp(0, n - 1)]
+        return torch.where(k[None, :] < cnt[:, None], rows, torch.full_like(rows, -1))
 
     def count_links(self):
         return int(self.t["cnt"][:self.n].clamp(max=self.K).sum(dtype=torch.int64).item())

@@ -18,10 +18,17 @@ class Box(object):
 
 
 class PeriodicBox(Box):
-    """box.py:28-47: a coordinate past a face is reset to the opposite face (not wrapped)."""
+    """box.py:28-47: a coordinate past a face is reset to the opposite face (not wrapped) -- the reference's
+    behaviour and the default.  `wrap=True` is the true periodic image instead (x - L * floor(x / L): a particle
+    that leaves through a face re-enters at the distance it overshot by), which is what conserves the pair
+    geometry of a periodic run; it is NOT what the reference computes, hence a flag."""
+
+    def __init__(self, p='none', xmax=64, ymax=48, zmax=100, wrap=False):
+        Box.__init__(self, p=p, xmax=xmax, ymax=ymax, zmax=zmax)
+        self.wrap = bool(wrap)
 
     def apply(self, p):
-        _backend.box_apply((self.xmax, self.ymax, self.zmax), 1, p.r, p.v, p.n)
+        _backend.box_apply((self.xmax, self.ymax, self.zmax), 2 if self.wrap else 1, p.r, p.v, p.n)
 
 
 class MirrorBox(Box):

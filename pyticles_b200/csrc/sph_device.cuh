@@ -87,6 +87,7 @@ struct CellLoc {
     uint32_t code;
     float rx, ry, rz;
     uint32_t flags;
+    int cx;              // local x cell layer (the slab decomposition's boundary layers are picked by it)
     bool interior;       // every dimension: >= 5 layers and not the first or last GLOBAL layer
 };
 
@@ -149,6 +150,7 @@ __device__ __forceinline__ CellLoc locate(const sph_grid &g, double x, double y,
     const int cc[3] = {cell_coord(g, 0, x, c.rx, c.flags), cell_coord(g, 1, y, c.ry, c.flags),
                        cell_coord(g, 2, z, c.rz, c.flags)};
     c.code = cell_code(g, cc[0], cc[1], cc[2]);
+    c.cx = cc[0];
     c.interior = true;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {

@@ -67,21 +67,51 @@ namespace {
 constexpr int kPPBlock = SPH_PP_BLOCK;
 
 
+// Particles [first, first + count).  Slots >= *n_valid (the unused part of the fixed-capacity ghost region of the
+// slab decomposition) go to the spare cell g.ncode, which no pass visits.  With index lists given, the particles of
+// local x layers 1 and ncl[0] - 2 (the slab's boundary layers) are appended to them, in arrival order.
+struct HaloLists {
+    int32_t *idx_left, *idx_right;
+    uint32_t cap;
+};
+
 __global__ void __launch_bounds__(kBlock)
-bin_kernel(const __grid_constant__ sph_grid g, const double *__restrict__ r, int n,
-           uint32_t *__restrict__ cell_count, uint32_t *__restrict__ code,
-           uint32_t *__restrict__ rank, sph_status *__restrict__ status)
+bin_kernel(const __grid_constant__ sph_grid g, const double *__restrict__ r, int first, int count,
+           const int32_t *__restrict__ n_valid, uint32_t *__restrict__ cell_count, uint32_t *__restrict__ code,
+           uint32_t *__restrict__ rank, sph_status *__restrict__ status, HaloLists hl)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = first + k;
     uint32_t flags = 0;
-    if (i < n) {
-        const CellLoc c = locate(g, r[3 * (size_t)i], r[3 * (size_t)i + 1], r[3 * (size_t)i + 2]);
-        flags = c.flags;
-        code[i] = c.code;
-        rank[i] = atomicAdd(cell_count + c.code, 1u);
+    bool left = false, right = false;
+    if (k < count) {
+        if (n_valid && i >= *n_valid) {
+            code[i] = g.ncode;
+            rank[i] = atomicAdd(cell_count + g.ncode, 1u);
+        } else {
+            const CellLoc c = locate(g, r[3 * (size_t)i], r[3 * (size_t)i + 1], r[3 * (size_t)i + 2]);
+            flags = c.flags;
+            code[i] = c.code;
+            rank[i] = atomicAdd(cell_count + c.code, 1u);
+            left = c.cx == 1;
+            right = c.cx == g.ncl[0] - 2;
+        }
     }
     flags = __reduce_or_sync(0xffffffffu, flags);
     if (flags && (threadIdx.x & 31) == 0) atomicOr(&status->flags, flags);
+    if (hl.idx_left) {
+        const uint32_t ml = __ballot_sync(0xffffffffu, left), mr = __ballot_sync(0xffffffffu, right);
+        const int lane = threadIdx.x & 31;
+        uint32_t bl = 0, br = 0;
+        if (lane == 0) {
+            if (ml) bl = atomicAdd(&status->halo_count[0], (uint32_t)__popc(ml));
+            if (mr) br = atomicAdd(&status->halo_count[1], (uint32_t)__popc(mr));
+        }
+        bl = __shfl_sync(0xffffffffu, bl, 0) + __popc(ml & ((1u << lane) - 1u));
+        br = __shfl_sync(0xffffffffu, br, 0) + __popc(mr & ((1u << lane) - 1u));
+        if (left && bl < hl.cap) hl.idx_left[bl] = i;
+        if (right && br < hl.cap) hl.idx_right[br] = i;
+    }
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -93,17 +123,25 @@ scatter_kernel(int n, const uint32_t *__restrict__ code, const uint32_t *__restr
 }
 
 // Arrival order inside a cell comes from atomics; make it canonical (ascending original
-// index) so that every later sum runs in a fixed order.
+// index; ghosts of the slab decomposition, whose slots depend on the neighbour rank's packing order,
+// by their global id) so that every later sum runs in a fixed order.
+__device__ __forceinline__ long long sort_key_of(int32_t v, int n_owned, const int64_t *__restrict__ key)
+{
+    return (key && n_owned > 0 && v >= n_owned) ? (1ll << 62) + (long long)key[v] : (long long)v;
+}
+
 __global__ void __launch_bounds__(kBlock)
-cell_sort_kernel(uint32_t ncode, const uint32_t *__restrict__ cell_start, int32_t *__restrict__ perm)
+cell_sort_kernel(uint32_t ncode, const uint32_t *__restrict__ cell_start, int32_t *__restrict__ perm, int n_owned,
+                 const int64_t *__restrict__ key)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncode) return;
     const uint32_t s = cell_start[c], e = cell_start[c + 1];
     for (uint32_t k = s + 1; k < e; ++k) {
         const int32_t v = perm[k];
+        const long long kv = sort_key_of(v, n_owned, key);
         uint32_t q = k;
-        while (q > s && perm[q - 1] > v) { perm[q] = perm[q - 1]; --q; }
+        while (q > s && sort_key_of(perm[q - 1], n_owned, key) > kv) { perm[q] = perm[q - 1]; --q; }
         perm[q] = v;
     }
 }
@@ -198,10 +236,18 @@ __global__ void __launch_bounds__(kBlock)
 gather_kernel(const __grid_constant__ sph_grid g, int n, const int32_t *__restrict__ perm,
               const double *__restrict__ r, const double *__restrict__ v,
               const double *__restrict__ m, double *__restrict__ pos4, double *__restrict__ vel4,
-              float *__restrict__ rel4)
+              float *__restrict__ rel4, int32_t *__restrict__ cnt, const uint32_t *__restrict__ cell_start)
 {
+    const uint32_t n_live = cell_start[g.ncode];       // particles in real cells
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= n) return;
+    if ((uint32_t)a >= n_live) {                       // unused ghost slot: no position, no neighbours
+        store4(pos4 + 4 * (size_t)a, 0.0, 0.0, 0.0, 0.0);
+        store4(vel4 + 4 * (size_t)a, 0.0, 0.0, 0.0, 0.0);
+        reinterpret_cast<float4 *>(rel4)[a] = make_float4(0.f, 0.f, 0.f, 0.f);
+        cnt[a] = 0;
+        return;
+    }
     const size_t i = (size_t)perm[a];
     const double x = r[3 * i], y = r[3 * i + 1], z = r[3 * i + 2];
     const CellLoc c = locate(g, x, y, z);
@@ -231,7 +277,7 @@ __global__ void __launch_bounds__(kNlWarps * 32)
 nlist_kernel(const __grid_constant__ sph_grid g, int n, int K,
              const uint32_t *__restrict__ cell_start, const float *__restrict__ rel4,
              const double *__restrict__ pos4, int32_t *__restrict__ nbr, int32_t *__restrict__ cnt,
-             sph_status *__restrict__ status, int only_fallback)
+             sph_status *__restrict__ status, int only_fallback, const int32_t *__restrict__ perm, int n_owned)
 {
     extern __shared__ float4 smem_cand[];
     // behind the tile kernels this pass only runs when they gave up (sph_tiles.cu)
@@ -253,6 +299,14 @@ nlist_kernel(const __grid_constant__ sph_grid g, int n, int K,
     for (uint32_t c = blockIdx.x * kNlWarps + wib; c < g.ncode; c += nwarps) {
         const uint32_t cs = cell_start[c], ce = cell_start[c + 1];
         if (cs == ce) continue;
+        if (n_owned > 0) {                                 // a cell of ghosts: no rows are built for them
+            bool ghosts = true;
+            for (uint32_t k = cs + lane; k < ce; k += 32) ghosts = ghosts && perm[k] >= n_owned;
+            if (__all_sync(0xffffffffu, ghosts)) {
+                for (uint32_t k = cs + lane; k < ce; k += 32) cnt[k] = 0;
+                continue;
+            }
+        }
         uint32_t nstart = 0, ncount = 0;
         float fx = 0.f, fy = 0.f, fz = 0.f;
         if (lane < 27) {
@@ -519,7 +573,7 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
                double *__restrict__ vel4, const float *__restrict__ rel4,
                const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
                const int32_t *__restrict__ cnt, const sph_status *__restrict__ status,
-               const double *__restrict__ h_orig, sph_eos eos, int list_fresh, int long_range,
+               const double *__restrict__ h_orig, sph_eos eos, int list_fresh, int long_range, int n_owned,
                double *__restrict__ rho_out, double *__restrict__ p_out, double *__restrict__ pco_out,
                double *__restrict__ u_out, double *__restrict__ t_io)
 {
@@ -531,8 +585,8 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
     bool interior = true;
     if (active) {
         load4(pos4 + 4 * (size_t)a, ax, ay, az, am);
-        count = min(cnt[a], K);
         orig = perm[a];
+        count = (n_owned > 0 && orig >= n_owned) ? 0 : min(cnt[a], K);       // nothing is computed for ghosts
         interior = cell_is_interior(g, __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w));
     }
     const bool can_skip = list_fresh && !(status->flags & (SPH_F_OUT_OF_BOX | SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
@@ -546,7 +600,7 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
     else sum = density_row<UNIFORM_H, true>(g, pos4, perm, h_orig, row, (size_t)32 * LPP, mine, orig, a, ax, ay, az, hinv, qn);
 #pragma unroll
     for (int o = 1; o < LPP; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (!active || q != 0) return;
+    if (!active || q != 0 || (n_owned > 0 && orig >= n_owned)) return;
     // properties.py:76-77: every particle starts from W(0; h[0]) -- not m_i * W(0; h_i)
     const double rho = qn + sum;
     rho_out[orig] = rho;
@@ -657,7 +711,7 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
              const double *__restrict__ vel4, const float *__restrict__ rel4,
              const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
              const int32_t *__restrict__ cnt, const sph_status *__restrict__ status,
-             const double *__restrict__ h_orig, int list_fresh, double fcutsq, int dim,
+             const double *__restrict__ h_orig, int list_fresh, double fcutsq, int dim, int n_owned, int store,
              double *__restrict__ vdot, double *__restrict__ udot)
 {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -669,8 +723,8 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
     if (active) {
         load4(pos4 + 4 * (size_t)a, px, py, pz, pm);
         load4(vel4 + 4 * (size_t)a, vx, vy, vz, Ai);
-        count = min(cnt[a], K);
         orig = perm[a];
+        count = (n_owned > 0 && orig >= n_owned) ? 0 : min(cnt[a], K);       // nothing is computed for ghosts
         interior = cell_is_interior(g, __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w));
     }
     const bool can_skip = list_fresh && !(status->flags & (SPH_F_OUT_OF_BOX | SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
@@ -689,13 +743,21 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
         f.az += __shfl_xor_sync(0xffffffffu, f.az, o);
         f.du += __shfl_xor_sync(0xffffffffu, f.du, o);
     }
-    if (!active || q != 0) return;
+    if (!active || q != 0 || (n_owned > 0 && orig >= n_owned)) return;
     (void)pm;
-    // the reference accumulates into vdot/udot (particles.py:549-550 zeroes them per evaluation)
-    vdot[3 * (size_t)orig] += f.ax;
-    vdot[3 * (size_t)orig + 1] += f.ay;
-    vdot[3 * (size_t)orig + 2] += f.az;
-    udot[orig] += f.du;
+    // the reference accumulates into vdot/udot (particles.py:549-550 zeroes them per evaluation); `store` says this
+    // is the first force after that zeroing, so the fill and the read-modify-write are both saved (0 + x == x)
+    if (store) {
+        vdot[3 * (size_t)orig] = f.ax;
+        vdot[3 * (size_t)orig + 1] = f.ay;
+        vdot[3 * (size_t)orig + 2] = f.az;
+        udot[orig] = f.du;
+    } else {
+        vdot[3 * (size_t)orig] += f.ax;
+        vdot[3 * (size_t)orig + 1] += f.ay;
+        vdot[3 * (size_t)orig + 2] += f.az;
+        udot[orig] += f.du;
+    }
 }
 
 // ------------------------------------------------------------------ heat conduction (c_forces.pyx:196-239)
@@ -981,95 +1043,101 @@ box_kernel(double Lx, double Ly, double Lz, int kind, double *__restrict__ r, do
         if (kind == 0) {                                   // box.py:53-73 MirrorBox
             if (x > L[d]) { x = L[d]; v[3 * (size_t)i + d] = -v[3 * (size_t)i + d]; }
             if (x < 0) { x = 0; v[3 * (size_t)i + d] = -v[3 * (size_t)i + d]; }
-        } else {                                           // box.py:35-47 PeriodicBox
+        } else if (kind == 1) {                            // box.py:35-47 PeriodicBox
             if (x > L[d]) x = 0;
             if (x < 0) x = L[d];
+        } else {                                           // true periodic image (not the reference's reset)
+            if (x >= L[d] || x < 0) {
+                x -= L[d] * floor(x / L[d]);
+                if (x >= L[d]) x = 0;                      // -tiny + L rounds to L
+            }
         }
         r[3 * (size_t)i + d] = x;
     }
 }
 
-// Slab decomposition: indices of the particles in the two boundary cell layers of this rank's slab.
+// ------------------------------------------------------------------ slab decomposition: ghost exchange
+// Fixed-capacity buffers with the count in a header row, so that no count travels to the host.  blockIdx.y = side
+// (0: towards the left neighbour, 1: towards the right one).
+constexpr int kHaloCols = SPH_HALO_COLS;
+
 __global__ void __launch_bounds__(kBlock)
-slab_select_kernel(const double *__restrict__ x, int64_t stride, int n, double inv_w, int nc, int lay_left,
-                   int lay_right, int32_t *__restrict__ idx_left, int32_t *__restrict__ idx_right,
-                   uint32_t cap, uint32_t *__restrict__ counts)
+halo_pack_kernel(sph_fields f, const int32_t *__restrict__ idx_left, const int32_t *__restrict__ idx_right,
+                 uint32_t cap, double *__restrict__ send_left, double *__restrict__ send_right,
+                 sph_status *__restrict__ status)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool l = false, r = false;
-    if (i < n) {
-        double f = floor(x[(size_t)i * stride] * inv_w);            // bin_kernel's own formula
-        if (!(fabs(f) < 4.0e15)) f = 0.0;
-        long long c = (long long)f % nc;
-        if (c < 0) c += nc;
-        l = (int)c == lay_left;
-        r = (int)c == lay_right;
+    const int side = blockIdx.y;
+    const uint32_t have = status->halo_count[side], cnt = have < cap ? have : cap;
+    const int32_t *idx = side ? idx_right : idx_left;
+    double *rows = side ? send_right : send_left;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) {
+        rows[0] = (double)cnt;
+        rows[1] = (double)have;
+#pragma unroll
+        for (int c = 2; c < kHaloCols; ++c) rows[c] = 0.0;
+        if (have > cap) atomicOr(&status->flags, SPH_F_HALO_OVERFLOW);
     }
-    const uint32_t ml = __ballot_sync(0xffffffffu, l), mr = __ballot_sync(0xffffffffu, r);
-    const int lane = threadIdx.x & 31;
-    uint32_t bl = 0, br = 0;
-    if (lane == 0) {
-        if (ml) bl = atomicAdd(counts, (uint32_t)__popc(ml));
-        if (mr) br = atomicAdd(counts + 1, (uint32_t)__popc(mr));
+    if (k >= cnt) return;
+    const size_t i = (size_t)idx[k];
+    double *o = rows + kHaloCols * ((size_t)k + 1);
+    o[0] = f.r[3 * i]; o[1] = f.r[3 * i + 1]; o[2] = f.r[3 * i + 2];
+    o[3] = f.v[3 * i]; o[4] = f.v[3 * i + 1]; o[5] = f.v[3 * i + 2];
+    o[6] = f.m[i]; o[7] = f.h[i]; o[8] = f.t[i];
+    o[9] = (double)f.gid[i];
+}
+
+// The left neighbour's particles fill the slots first .. first + cL - 1, the right neighbour's the cR behind them.
+__global__ void __launch_bounds__(kBlock)
+halo_unpack_kernel(sph_fields f, const double *__restrict__ recv_left, const double *__restrict__ recv_right,
+                   uint32_t cap, int first, int32_t *__restrict__ n_valid, sph_status *__restrict__ status)
+{
+    const int side = blockIdx.y;
+    uint32_t cL = (uint32_t)recv_left[0], cR = (uint32_t)recv_right[0];
+    cL = cL < cap ? cL : cap;
+    cR = cR < cap ? cR : cap;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0 && side == 0) {
+        *n_valid = first + (int)(cL + cR);
+        status->ghost_count[0] = cL;
+        status->ghost_count[1] = cR;
     }
-    bl = __shfl_sync(0xffffffffu, bl, 0);
-    br = __shfl_sync(0xffffffffu, br, 0);
-    const uint32_t lt = (1u << lane) - 1u;
-    if (l && bl + __popc(ml & lt) < cap) idx_left[bl + __popc(ml & lt)] = i;
-    if (r && br + __popc(mr & lt) < cap) idx_right[br + __popc(mr & lt)] = i;
-}
-
-// Halo exchange of the slab decomposition: one row of 10 doubles per boundary particle
-// (r, v, m, h, t, global id), packed / unpacked in one pass each instead of a dozen tensor operations.
-__global__ void __launch_bounds__(kBlock)
-halo_pack_kernel(const int64_t *__restrict__ idx, int64_t n, const double *__restrict__ r,
-                 const double *__restrict__ v, const double *__restrict__ m, const double *__restrict__ h,
-                 const double *__restrict__ t, const int64_t *__restrict__ gid, double *__restrict__ rows)
-{
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const size_t i = (size_t)idx[k];
-    double *o = rows + 10 * (size_t)k;
-    o[0] = r[3 * i]; o[1] = r[3 * i + 1]; o[2] = r[3 * i + 2];
-    o[3] = v[3 * i]; o[4] = v[3 * i + 1]; o[5] = v[3 * i + 2];
-    o[6] = m[i]; o[7] = h[i]; o[8] = t[i];
-    o[9] = (double)gid[i];
+    if (k >= (side ? cR : cL)) return;
+    const double *o = (side ? recv_right : recv_left) + kHaloCols * ((size_t)k + 1);
+    const size_t i = (size_t)first + (side ? cL : 0u) + k;
+    f.r[3 * i] = o[0]; f.r[3 * i + 1] = o[1]; f.r[3 * i + 2] = o[2];
+    f.v[3 * i] = o[3]; f.v[3 * i + 1] = o[4]; f.v[3 * i + 2] = o[5];
+    f.m[i] = o[6]; f.h[i] = o[7]; f.t[i] = o[8];
+    f.gid[i] = (int64_t)o[9];
 }
 
 __global__ void __launch_bounds__(kBlock)
-halo_unpack_kernel(const double *__restrict__ rows, int64_t n, int64_t first, double *__restrict__ r,
-                   double *__restrict__ v, double *__restrict__ m, double *__restrict__ h,
-                   double *__restrict__ t, int64_t *__restrict__ gid)
+halo_pack2_kernel(const int32_t *__restrict__ idx_left, const int32_t *__restrict__ idx_right, uint32_t cap,
+                  const double *__restrict__ a, const double *__restrict__ b, double *__restrict__ send_left,
+                  double *__restrict__ send_right, const sph_status *__restrict__ status)
 {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const size_t i = (size_t)(first + k);
-    const double *o = rows + 10 * (size_t)k;
-    r[3 * i] = o[0]; r[3 * i + 1] = o[1]; r[3 * i + 2] = o[2];
-    v[3 * i] = o[3]; v[3 * i + 1] = o[4]; v[3 * i + 2] = o[5];
-    m[i] = o[6]; h[i] = o[7]; t[i] = o[8];
-    gid[i] = (int64_t)o[9];
+    const int side = blockIdx.y;
+    const uint32_t have = status->halo_count[side], cnt = have < cap ? have : cap;
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt) return;
+    const size_t i = (size_t)(side ? idx_right : idx_left)[k];
+    double *o = (side ? send_right : send_left) + 2 * (size_t)k;
+    o[0] = a[i];
+    o[1] = b[i];
 }
 
 __global__ void __launch_bounds__(kBlock)
-halo_pack2_kernel(const int64_t *__restrict__ idx, int64_t n, const double *__restrict__ a,
-                  const double *__restrict__ b, double *__restrict__ out)
+halo_unpack2_kernel(const double *__restrict__ recv_left, const double *__restrict__ recv_right, int first,
+                    double *__restrict__ a, double *__restrict__ b, const sph_status *__restrict__ status)
 {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    const size_t i = (size_t)idx[k];
-    out[2 * k] = a[i];
-    out[2 * k + 1] = b[i];
-}
-
-__global__ void __launch_bounds__(kBlock)
-halo_unpack2_kernel(const double *__restrict__ in, int64_t n, int64_t first, double *__restrict__ a,
-                    double *__restrict__ b)
-{
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    a[first + k] = in[2 * k];
-    b[first + k] = in[2 * k + 1];
+    const int side = blockIdx.y;
+    const uint32_t cL = status->ghost_count[0], cR = status->ghost_count[1];
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= (side ? cR : cL)) return;
+    const double *o = (side ? recv_right : recv_left) + 2 * (size_t)k;
+    const size_t i = (size_t)first + (side ? cL : 0u) + k;
+    a[i] = o[0];
+    b[i] = o[1];
 }
 
 inline int blocks_for(int64_t n, int per) { return (int)((n + per - 1) / per); }
@@ -1116,11 +1184,13 @@ constexpr double kCellTarget = 8.0;    // particles per cell the planner widens 
 // ====================================================================== C ABI
 extern "C" {
 
-const char *sph_version(void) { return "pyticles_b200 0.2 (sm_100a, abi 2)"; }
+#define SPH_STR2(x) #x
+#define SPH_STR(x) SPH_STR2(x)
+const char *sph_version(void) { return "pyticles_b200 0.3 (sm_100a, abi " SPH_STR(SPH_ABI_VERSION) ")"; }
 
 int64_t sph_scan_tmp_elems(uint32_t ncode)
 {
-    return ((int64_t)ncode + kScanTile - 1) / kScanTile + 2;
+    return ((int64_t)ncode + kScanTile - 1) / kScanTile + 3;
 }
 
 int64_t sph_nbr_elems(int32_t n, int32_t max_nbrs)
@@ -1304,32 +1374,69 @@ int sph_exclusive_scan_u32(const uint32_t *d_in, uint32_t *d_out, uint32_t *d_tm
     return launch_status();
 }
 
-int sph_cells_build(const sph_grid *g, const sph_buffers *b, const double *d_r, void *stream)
+static bool cells_args_ok(const sph_grid *g, const sph_buffers *b, const double *d_r)
 {
-    if (!g || !b || !d_r || b->n < 0) return SPH_E_BADARG;
-    if (!b->cell_count || !b->cell_start || !b->scan_tmp || !b->code || !b->rank || !b->perm || !b->status)
+    return g && b && d_r && b->n >= 0 && b->cell_count && b->cell_start && b->scan_tmp && b->code && b->rank &&
+           b->perm && b->status;
+}
+
+int sph_cells_begin(const sph_grid *g, const sph_buffers *b, const double *d_r, int32_t first, int32_t count,
+                    int32_t *d_idx_left, int32_t *d_idx_right, int32_t cap, void *stream)
+{
+    if (!cells_args_ok(g, b, d_r) || first < 0 || count < 0 || first + count > b->n || cap < 0) return SPH_E_BADARG;
+    if ((d_idx_left == nullptr) != (d_idx_right == nullptr)) return SPH_E_BADARG;
+    if (d_idx_left && (g->wrap[0] || g->ncl[0] < 4)) return SPH_E_BADARG;     // needs a restricted slab grid
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaMemsetAsync(b->cell_count, 0, sizeof(uint32_t) * ((size_t)g->ncode + 1), s);
+    const HaloLists hl = {d_idx_left, d_idx_right, (uint32_t)cap};
+    if (count > 0)
+        bin_kernel<<<blocks_for(count, kBlock), kBlock, 0, s>>>(*g, d_r, first, count, b->n_valid, b->cell_count,
+                                                                b->code, b->rank, b->status, hl);
+    return launch_status();
+}
+
+int sph_cells_add(const sph_grid *g, const sph_buffers *b, const double *d_r, int32_t first, int32_t count,
+                  void *stream)
+{
+    if (!cells_args_ok(g, b, d_r) || first < 0 || count < 0 || first + count > b->n) return SPH_E_BADARG;
+    const HaloLists hl = {nullptr, nullptr, 0u};
+    if (count > 0)
+        bin_kernel<<<blocks_for(count, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+            *g, d_r, first, count, b->n_valid, b->cell_count, b->code, b->rank, b->status, hl);
+    return launch_status();
+}
+
+int sph_cells_finish(const sph_grid *g, const sph_buffers *b, void *stream)
+{
+    if (!g || !b || !b->cell_count || !b->cell_start || !b->scan_tmp || !b->code || !b->rank || !b->perm)
         return SPH_E_BADARG;
     cudaStream_t s = (cudaStream_t)stream;
-    cudaMemsetAsync(b->cell_count, 0, sizeof(uint32_t) * (size_t)g->ncode, s);
-    if (b->n > 0)
-        bin_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, s>>>(*g, d_r, b->n, b->cell_count, b->code,
-                                                               b->rank, b->status);
-    int rc = sph_exclusive_scan_u32(b->cell_count, b->cell_start, b->scan_tmp, g->ncode, stream);
+    // one cell more than the grid has: the spare cell of the unused ghost slots
+    int rc = sph_exclusive_scan_u32(b->cell_count, b->cell_start, b->scan_tmp, (int64_t)g->ncode + 1, stream);
     if (rc != SPH_OK) return rc;
     if (b->n > 0) {
         scatter_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, s>>>(b->n, b->code, b->rank, b->cell_start, b->perm);
-        cell_sort_kernel<<<blocks_for(g->ncode, kBlock), kBlock, 0, s>>>(g->ncode, b->cell_start, b->perm);
+        cell_sort_kernel<<<blocks_for(g->ncode, kBlock), kBlock, 0, s>>>(g->ncode, b->cell_start, b->perm, b->n_owned,
+                                                                        b->sort_key);
     }
     return launch_status();
+}
+
+int sph_cells_build(const sph_grid *g, const sph_buffers *b, const double *d_r, void *stream)
+{
+    if (!cells_args_ok(g, b, d_r)) return SPH_E_BADARG;
+    const int rc = sph_cells_begin(g, b, d_r, 0, b->n, nullptr, nullptr, 0, stream);
+    return rc != SPH_OK ? rc : sph_cells_finish(g, b, stream);
 }
 
 int sph_gather(const sph_grid *g, const sph_buffers *b, const double *d_r, const double *d_v,
                const double *d_m, void *stream)
 {
-    if (!g || !b || !d_r || !d_v || !d_m || !b->pos4 || !b->vel4 || !b->rel4 || !b->perm) return SPH_E_BADARG;
+    if (!g || !b || !d_r || !d_v || !d_m || !b->pos4 || !b->vel4 || !b->rel4 || !b->perm || !b->cnt || !b->cell_start)
+        return SPH_E_BADARG;
     if (b->n > 0)
         gather_kernel<<<blocks_for(b->n, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
-            *g, b->n, b->perm, d_r, d_v, d_m, b->pos4, b->vel4, b->rel4);
+            *g, b->n, b->perm, d_r, d_v, d_m, b->pos4, b->vel4, b->rel4, b->cnt, b->cell_start);
     return launch_status();
 }
 
@@ -1349,10 +1456,12 @@ static int nlist_general(const sph_grid *g, const sph_buffers *b, int only_fallb
     if (blocks > cap) blocks = cap;
     if (small)
         nlist_kernel<true><<<(unsigned)blocks, kNlWarps * 32, smem, s>>>(
-            *g, b->n, b->max_nbrs, b->cell_start, b->rel4, b->pos4, b->nbr, b->cnt, b->status, only_fallback);
+            *g, b->n, b->max_nbrs, b->cell_start, b->rel4, b->pos4, b->nbr, b->cnt, b->status, only_fallback, b->perm,
+            b->n_owned);
     else
         nlist_kernel<false><<<(unsigned)blocks, kNlWarps * 32, smem, s>>>(
-            *g, b->n, b->max_nbrs, b->cell_start, b->rel4, b->pos4, b->nbr, b->cnt, b->status, only_fallback);
+            *g, b->n, b->max_nbrs, b->cell_start, b->rel4, b->pos4, b->nbr, b->cnt, b->status, only_fallback, b->perm,
+            b->n_owned);
     return launch_status();
 }
 
@@ -1384,7 +1493,7 @@ int sph_density_eos(const sph_grid *g, const sph_buffers *b, const sph_eos *eos,
 #define SPH_LAUNCH_DENSITY(U, L)                                                                              \
     density_kernel<U, L><<<blocks_for((int64_t)b->n * L, kPPBlock), kPPBlock, 0, s>>>(                        \
         *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig, *eos, \
-        list_fresh, use_hlr, d_rho, d_p, d_pco, d_u, d_t)
+        list_fresh, use_hlr, b->n_owned, d_rho, d_p, d_pco, d_u, d_t)
     if (h_uniform) {
         if (lpp == 1) SPH_LAUNCH_DENSITY(true, 1);
         else if (lpp == 2) SPH_LAUNCH_DENSITY(true, 2);
@@ -1398,7 +1507,7 @@ int sph_density_eos(const sph_grid *g, const sph_buffers *b, const sph_eos *eos,
 }
 
 int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, const double *d_rho,
-              const double *d_h_orig, int h_uniform, int list_fresh, double fcutoff, int dim,
+              const double *d_h_orig, int h_uniform, int list_fresh, double fcutoff, int dim, int first_force,
               double *d_vdot, double *d_udot, void *stream)
 {
     if (!g || !b || !d_h_orig || !d_vdot || !d_udot) return SPH_E_BADARG;
@@ -1414,7 +1523,7 @@ int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, co
 #define SPH_LAUNCH_FORCE(U, L)                                                                                 \
     force_kernel<U, L><<<blocks_for((int64_t)b->n * L, kPPBlock), kPPBlock, 0, s>>>(                           \
         *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig,        \
-        list_fresh, fcutsq, dim, d_vdot, d_udot)
+        list_fresh, fcutsq, dim, b->n_owned, first_force ? 1 : 0, d_vdot, d_udot)
     if (h_uniform) {
         if (lpp == 1) SPH_LAUNCH_FORCE(true, 1);
         else if (lpp == 2) SPH_LAUNCH_FORCE(true, 2);
@@ -1515,52 +1624,51 @@ int sph_ponder_rebuild(const double *d_r_old, const double *d_r, int32_t n, doub
     return launch_status();
 }
 
-int sph_slab_select(const double *d_x, int64_t stride, int32_t n, double inv_w, int32_t nc,
-                    int32_t layer_left, int32_t layer_right, int32_t *d_idx_left, int32_t *d_idx_right,
-                    int32_t cap, uint32_t *d_counts, void *stream)
+static bool fields_ok(const sph_fields *f)
 {
-    if (n < 0 || nc <= 0 || cap < 0 || !d_counts || (n > 0 && (!d_x || !d_idx_left || !d_idx_right))) return SPH_E_BADARG;
-    cudaStream_t s = (cudaStream_t)stream;
-    cudaMemsetAsync(d_counts, 0, 2 * sizeof(uint32_t), s);
-    if (n > 0)
-        slab_select_kernel<<<blocks_for(n, kBlock), kBlock, 0, s>>>(d_x, stride, n, inv_w, nc, layer_left,
-                                                                    layer_right, d_idx_left, d_idx_right, (uint32_t)cap, d_counts);
+    return f && f->r && f->v && f->m && f->h && f->t && f->gid;
+}
+
+int sph_halo_pack(const sph_fields *f, const int32_t *d_idx_left, const int32_t *d_idx_right, int32_t cap,
+                  double *d_send_left, double *d_send_right, sph_status *d_status, void *stream)
+{
+    if (!fields_ok(f) || !d_idx_left || !d_idx_right || cap <= 0 || !d_send_left || !d_send_right || !d_status)
+        return SPH_E_BADARG;
+    const dim3 grid((unsigned)blocks_for(cap, kBlock), 2u);
+    halo_pack_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(*f, d_idx_left, d_idx_right, (uint32_t)cap, d_send_left,
+                                                                d_send_right, d_status);
     return launch_status();
 }
 
-int sph_halo_pack(const int64_t *d_idx, int64_t n_idx, const double *d_r, const double *d_v, const double *d_m,
-                  const double *d_h, const double *d_t, const int64_t *d_gid, double *d_rows, void *stream)
+int sph_halo_unpack(const sph_fields *f, const double *d_recv_left, const double *d_recv_right, int32_t cap,
+                    int32_t first, int32_t *d_n_valid, sph_status *d_status, void *stream)
 {
-    if (n_idx < 0 || (n_idx > 0 && (!d_idx || !d_r || !d_v || !d_m || !d_h || !d_t || !d_gid || !d_rows))) return SPH_E_BADARG;
-    if (n_idx > 0)
-        halo_pack_kernel<<<blocks_for(n_idx, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_idx, n_idx, d_r, d_v, d_m, d_h,
-                                                                                        d_t, d_gid, d_rows);
+    if (!fields_ok(f) || !d_recv_left || !d_recv_right || cap <= 0 || first < 0 || !d_n_valid || !d_status)
+        return SPH_E_BADARG;
+    const dim3 grid((unsigned)blocks_for(cap, kBlock), 2u);
+    halo_unpack_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(*f, d_recv_left, d_recv_right, (uint32_t)cap, first,
+                                                                  d_n_valid, d_status);
     return launch_status();
 }
 
-int sph_halo_unpack(const double *d_rows, int64_t n_rows, int64_t first, double *d_r, double *d_v, double *d_m,
-                    double *d_h, double *d_t, int64_t *d_gid, void *stream)
+int sph_halo_pack2(const int32_t *d_idx_left, const int32_t *d_idx_right, int32_t cap, const double *d_a,
+                   const double *d_b, double *d_send_left, double *d_send_right, const sph_status *d_status,
+                   void *stream)
 {
-    if (n_rows < 0 || first < 0 || (n_rows > 0 && (!d_rows || !d_r || !d_v || !d_m || !d_h || !d_t || !d_gid))) return SPH_E_BADARG;
-    if (n_rows > 0)
-        halo_unpack_kernel<<<blocks_for(n_rows, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_rows, n_rows, first, d_r, d_v,
-                                                                                           d_m, d_h, d_t, d_gid);
+    if (!d_idx_left || !d_idx_right || cap <= 0 || !d_a || !d_b || !d_send_left || !d_send_right || !d_status)
+        return SPH_E_BADARG;
+    const dim3 grid((unsigned)blocks_for(cap, kBlock), 2u);
+    halo_pack2_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(d_idx_left, d_idx_right, (uint32_t)cap, d_a, d_b,
+                                                                 d_send_left, d_send_right, d_status);
     return launch_status();
 }
 
-int sph_halo_pack2(const int64_t *d_idx, int64_t n_idx, const double *d_a, const double *d_b, double *d_out, void *stream)
+int sph_halo_unpack2(const double *d_recv_left, const double *d_recv_right, int32_t cap, int32_t first,
+                     double *d_a, double *d_b, const sph_status *d_status, void *stream)
 {
-    if (n_idx < 0 || (n_idx > 0 && (!d_idx || !d_a || !d_b || !d_out))) return SPH_E_BADARG;
-    if (n_idx > 0)
-        halo_pack2_kernel<<<blocks_for(n_idx, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_idx, n_idx, d_a, d_b, d_out);
-    return launch_status();
-}
-
-int sph_halo_unpack2(const double *d_in, int64_t n_rows, int64_t first, double *d_a, double *d_b, void *stream)
-{
-    if (n_rows < 0 || first < 0 || (n_rows > 0 && (!d_in || !d_a || !d_b))) return SPH_E_BADARG;
-    if (n_rows > 0)
-        halo_unpack2_kernel<<<blocks_for(n_rows, kBlock), kBlock, 0, (cudaStream_t)stream>>>(d_in, n_rows, first, d_a, d_b);
+    if (!d_recv_left || !d_recv_right || cap <= 0 || first < 0 || !d_a || !d_b || !d_status) return SPH_E_BADARG;
+    const dim3 grid((unsigned)blocks_for(cap, kBlock), 2u);
+    halo_unpack2_kernel<<<grid, kBlock, 0, (cudaStream_t)stream>>>(d_recv_left, d_recv_right, first, d_a, d_b, d_status);
     return launch_status();
 }
 

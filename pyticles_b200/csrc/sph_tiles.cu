@@ -52,6 +52,8 @@ struct TileArgs {
     sph_status *status;
     float thr_in, thr_out;
     int pass0;               // particles of a cell per pass to start with (16 or 8)
+    const int32_t *perm;
+    int n_owned;             // > 0: cells of ghosts (original index >= n_owned) get empty rows
 };
 
 // shared memory of a block: [S32 | B | Head]
@@ -233,6 +235,14 @@ __device__ __forceinline__ uint32_t tile_cell(const sph_grid &g, const TileArgs 
         if (lane == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
         return 0u;
     }
+    if (a.n_owned > 0) {                                                 // slab decomposition: no rows for ghosts
+        bool ghosts = true;
+        for (int k = lane; k < hc.P; k += 32) ghosts = ghosts && a.perm[hc.cs + k] >= a.n_owned;
+        if (__all_sync(kFull, ghosts)) {
+            for (int k = lane; k < hc.P; k += 32) a.cnt[hc.cs + k] = 0;
+            return 0u;
+        }
+    }
     entry_t *B = reinterpret_cast<entry_t *>(smem + kBytesS32) + (w * 32 + lane) * kTRowS;     // this lane's list of hits
     const uint32_t s32a = smem_u32(S32), s16 = s32a & 0xffffu;
     const uint32_t lp0 = smem_u32(B), lp_lim = lp0 + (uint32_t)sizeof(entry_t) * kTRow;
@@ -384,6 +394,8 @@ TileArgs base_args(const sph_grid *g, const sph_buffers *b)
     a.nbr = b->nbr;
     a.cnt = b->cnt;
     a.status = b->status;
+    a.perm = b->perm;
+    a.n_owned = b->n_owned;
     tile_thresholds(g, &a.thr_in, &a.thr_out);
     // expected neighbours per particle at the mean density of the local grid: a stream of Q = 2 holds 32 hits
     const double vol = (g->ncl[0] * g->w[0]) * (g->ncl[1] * g->w[1]) * (g->ncl[2] * g->w[2]);

@@ -13,8 +13,7 @@ from .array import parray
 
 # launches of OUR kernels per evaluation: status_reset, bin, scan x3, scatter, cell_sort, gather (8);
 # flags_clear, tile_list, nlist (the general kernel behind the tile kernel: launched, returns at once
-# unless that one gave up) (3); density, force (2).  cudaMemset of the cell counters and the two
-# torch fills of vdot/udot are not counted.
+# unless that one gave up) (3); density, force (2).  The cudaMemset of the cell counters is not counted.
 LAUNCHES_PER_EVAL = 13
 
 
@@ -64,12 +63,11 @@ class SphEvaluator(object):
         be.nlist()
         if timed:
             ev[2].record()
-        x["vdot"].zero_()
-        x["udot"].zero_()
         be.density_eos(self.eos, x["h"], self.h_uniform, x["rho"], x["p"], x["pco"], x["u"], x["t"])
         if timed:
             ev[3].record()
-        be.force(None, None, x["h"], self.h_uniform, self.force.cutoff, 3, x["vdot"], x["udot"], reuse_press=True)
+        be.force(None, None, x["h"], self.h_uniform, self.force.cutoff, 3, x["vdot"], x["udot"], reuse_press=True,
+                 first_force=True)      # stores: the zeroing of particles.py:549-550 is folded into the kernel
         if timed:
             ev[4].record()
             self._events.append(ev)
@@ -106,17 +104,33 @@ class SphEvaluator(object):
     def pairs_per_particle(self):
         return self.nl.backend.count_links() / 2.0 / max(1, self.n_owned)
 
+    # ------------------------------------------------------------------ read-outs for bench.py's parity gate
+    def owned_state(self):
+        """r, v, t and the global id (= index) of the owned particles."""
+        p, n = self.p, self.p.n
+        T = lambda x: x.as_subclass(torch.Tensor)[:n]
+        return {"r": T(p.r), "v": T(p.v), "t": T(p.t), "gid": torch.arange(n, dtype=torch.int64, device=p.r.device)}
+
+    def owned_results(self):
+        p, n = self.p, self.p.n
+        return {k: getattr(p, k).as_subclass(torch.Tensor)[:n] for k in ("rho", "p", "vdot", "udot")}
+
+    def neighbour_gids(self, idx):
+        return self.nl.backend.neighbour_rows(idx)
+
     # ------------------------------------------------------------------ end to end with host buffers
     def run_e2e(self, steps, warmup):
-        """Host-buffer path: every step copies that step's r, v, m, h, t from pinned host memory to
-        the device, evaluates, and copies rho, p, vdot, udot back to pinned host memory.  Frames are
+        """Host-buffer path: every step copies that step's r, v, t from pinned host memory to
+        the device, evaluates, and copies rho, p, vdot, udot back to pinned host memory.  m and h do not
+        change between the derivative evaluations of a run (the reference never touches them after set-up:
+        particles.py:122-127,323-343), so they are uploaded once and reported as `static`.  Frames are
         independent, so the three stages run as a pipeline over two device slots (copy-in of frame
         k+1 and copy-out of frame k-1 overlap the kernels of frame k on separate streams)."""
         p = self.p
-        ins, outs, alls = ("r", "v", "m", "h", "t"), ("rho", "p", "vdot", "udot"), \
+        ins, static, outs, alls = ("r", "v", "t"), ("m", "h"), ("rho", "p", "vdot", "udot"), \
             ("r", "v", "m", "h", "t", "rho", "p", "pco", "u", "vdot", "udot")
         base = {k: getattr(p, k).as_subclass(torch.Tensor) for k in alls}
-        slots = [base, {k: torch.empty_like(v) for k, v in base.items()}]
+        slots = [base, {k: (v if k in static else torch.empty_like(v)) for k, v in base.items()}]
         h_in = {k: torch.empty(base[k].shape, dtype=base[k].dtype, pin_memory=True).copy_(base[k]) for k in ins}
         h_out = {k: torch.empty(base[k].shape, dtype=base[k].dtype, pin_memory=True) for k in outs}
         h2d = sum(h_in[k].numel() * h_in[k].element_size() for k in ins)
@@ -163,7 +177,9 @@ class SphEvaluator(object):
         s_comp.wait_stream(s_in)
         t1.record(s_comp)
         torch.cuda.synchronize()
-        return {"ms": t0.elapsed_time(t1), "steps": steps, "h2d": h2d, "d2h": d2h}
+        stat = sum(base[k].numel() * base[k].element_size() for k in static)
+        return {"ms": t0.elapsed_time(t1), "steps": steps, "h2d": h2d, "d2h": d2h, "static": stat,
+                "out": {k: h_out[k] for k in outs}}
 
 
 def p_ver(t):

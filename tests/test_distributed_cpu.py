@@ -1,6 +1,9 @@
-"""CPU suite (gloo, world_size 2): the host-side logic of the slab decomposition --
-ownership by cell layer, migration, ghost exchange A/B and the pair-ownership rule --
-checked against the CPU oracle.  The CUDA passes themselves are covered by the gpu suite."""
+"""CPU suite (gloo, world_size 2, 3 and 4): the host-side logic of the slab decomposition --
+ownership by cell layer, migration, the fixed-capacity ring exchange A/B (the protocol the CUDA path uses) and the
+pair-ownership rule -- with the CPU oracle as the local "kernel": the global pair set must come out bit-exact and
+rho / p / vdot / udot of every particle within 1e-10 of the oracle on the whole box.  With three or more ranks the
+left and right neighbours differ, and rank 0 and rank W-1 meet across the periodic face.  The CUDA passes
+themselves are covered by the gpu suite."""
 import os
 import socket
 
@@ -25,36 +28,58 @@ def _free_port():
     return port
 
 
+def _inputs():
+    r, v, box = O.lattice_workload(24, 8, 8, seed=31, jitter=0.3)
+    n = r.shape[0]
+    rng = np.random.default_rng(9)
+    m = 1.0 + 0.1 * rng.random(n)
+    t = 1.0 + 0.2 * rng.random(n)
+    return r, v, m, np.full(n, 2.0), t
+
+
 def _worker(rank, world, port, out):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from pyticles_b200 import distributed as D
-        r, v, box = O.lattice_workload(24, 8, 8, seed=31, jitter=0.3)
+        r, v, m, h, t = _inputs()
         n = r.shape[0]
         gid = np.arange(n)
         mine = gid % world == rank                      # deliberately NOT spatial: migrate() must fix it
-        rows = D.make_rows(torch.from_numpy(r[mine]), torch.from_numpy(v[mine]), torch.ones(mine.sum(), dtype=torch.float64),
-                           torch.full((int(mine.sum()),), 2.0, dtype=torch.float64), torch.ones(mine.sum(), dtype=torch.float64),
-                           torch.from_numpy(gid[mine]))
+        T = torch.from_numpy
+        rows = D.make_rows(T(r[mine]), T(v[mine]), T(m[mine]), T(h[mine]), T(t[mine]), T(gid[mine]))
         dec = D.SlabDecomposition(BOX, CUTOFF, TOL, n)
-        res = {"rank": rank, "nc": dec.nc, "bounds": dec.bounds}
+        res = {"rank": rank, "nc": dec.nc, "bounds": dec.bounds, "nbrs": (dec.left, dec.right)}
         own = dec.migrate(rows)
         lay = dec.layer_of(own[:, D.C_R])
         res["own_ok"] = bool(((lay >= dec.lay0) & (lay < dec.lay1)).all())
         ghosts = dec.halo_exchange(own)
         gl = dec.layer_of(ghosts[:, D.C_R])
-        res["ghost_ok"] = bool(((gl == (dec.lay0 - 1) % dec.nc) | (gl == dec.lay1 % dec.nc)).all())
+        li, ri, cl, cr = dec._halo
+        # the left neighbour's last layer first, then the right neighbour's first layer
+        res["ghost_ok"] = bool((gl[:cl] == (dec.lay0 - 1) % dec.nc).all() and (gl[cl:] == dec.lay1 % dec.nc).all()
+                               and cl + cr == ghosts.shape[0] and cl > 0 and cr > 0)
         # exchange B must deliver columns of the same particles in the same order
         tag = torch.stack([own[:, D.C_GID] * 2 + 1, own[:, D.C_GID] * 3], dim=1)
         got = dec.halo_exchange_again(tag)
         res["b_ok"] = bool((got[:, 0] == ghosts[:, D.C_GID] * 2 + 1).all() and (got[:, 1] == ghosts[:, D.C_GID] * 3).all())
-        # local pairs by the oracle on owned + ghost particles, then the ownership rule
-        loc = torch.cat([own, ghosts])
-        no = own.shape[0]
-        iap = torch.from_numpy(C.build_pairs(loc[:, 0:3].numpy(), np.array(BOX), CUTOFF, TOL).astype(np.int64))
-        g = loc[:, D.C_GID].to(torch.int64)
+        # one derivative evaluation as SlabSphEvaluator.evaluate runs it, the oracle standing in for the kernels
+        loc = torch.cat([own, ghosts]).numpy()
+        no, nl = own.shape[0], own.shape[0] + ghosts.shape[0]
+        bx = np.array(BOX)
+        lr, lv = np.ascontiguousarray(loc[:, 0:3]), np.ascontiguousarray(loc[:, 3:6])
+        iap = C.build_pairs(lr, bx, CUTOFF, TOL)
+        drij, rij, rsq, dv = C.separations(iap, lr, lv, bx)
+        pr = C.density_eos(nl, loc[:, D.C_M], loc[:, D.C_H], loc[:, D.C_T], iap, rij, drij)
+        pb = dec.halo_exchange_again(torch.from_numpy(np.stack([pr["p"][:no], pr["rho"][:no]], axis=1)))    # B
+        press, rho = pr["p"].copy(), pr["rho"].copy()
+        press[no:], rho[no:] = pb[:, 0].numpy(), pb[:, 1].numpy()
+        vdot, udot = C.force(nl, loc[:, D.C_M], press, rho, iap, rij, pr["dwij"], dv, 5.0)
+        res.update(rho=pr["rho"][:no], p=pr["p"][:no], vdot=vdot[:no], udot=udot[:no])
+        # the ownership rule on the local pair list
+        iap = torch.from_numpy(iap.astype(np.int64))
+        g = torch.from_numpy(loc[:, D.C_GID]).to(torch.int64)
         gi, gj = g[iap[:, 0]], g[iap[:, 1]]
         keep = dec.owns_pair(gi, gj, iap[:, 0] < no, iap[:, 1] < no)
         pairs = torch.stack([torch.minimum(gi, gj)[keep], torch.maximum(gi, gj)[keep]], dim=1).numpy()
@@ -75,41 +100,68 @@ def _worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(300)
-def test_slab_decomposition_world2():
-    world = 2
+def _spawn(target, world, timeout=240):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, _free_port_once(), q)) for r in range(world)]
+    port = _free_port()
+    procs = [ctx.Process(target=target, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = q.get(timeout=240)
+    import queue
+    import time
+    res, t0 = None, time.time()
+    try:
+        while res is None:
+            try:
+                res = q.get(timeout=2.0)
+            except queue.Empty:
+                if time.time() - t0 > timeout or any(p.exitcode not in (None, 0) for p in procs):
+                    for p in procs:
+                        if p.is_alive():
+                            p.kill()
+                    raise AssertionError("a rank failed or timed out")
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
     for p in procs:
-        p.join(timeout=60)
         assert p.exitcode == 0
-    r, v, box = O.lattice_workload(24, 8, 8, seed=31, jitter=0.3)
-    ref = C.build_pairs(r, np.array(BOX), CUTOFF, TOL).astype(np.int64)
-    assert res[0]["nc"] == res[1]["nc"] and res[0]["bounds"] == res[1]["bounds"]
-    for x in res:
+    return res
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_slab_decomposition(world):
+    res = _spawn(_worker, world)
+    r, v, m, h, t = _inputs()
+    n = r.shape[0]
+    ref = C.sph_step(r, v, m, h, t, np.array(BOX), CUTOFF, TOL, 5.0)
+    assert all(x["nc"] == res[0]["nc"] and x["bounds"] == res[0]["bounds"] for x in res)
+    assert min(b - a for a, b in zip(res[0]["bounds"], res[0]["bounds"][1:])) >= 2
+    for k, x in enumerate(res):
         assert x["own_ok"] and x["ghost_ok"] and x["b_ok"] and x["own2_ok"]
+        assert x["nbrs"] == ((k - 1) % world, (k + 1) % world)
+    if world > 2:
+        assert all(x["nbrs"][0] != x["nbrs"][1] for x in res)          # a ring with distinct neighbours
     # every particle owned exactly once, before and after the move
     for key in ("gids", "gids2"):
         allg = np.sort(np.concatenate([x[key] for x in res]))
-        assert np.array_equal(allg, np.arange(r.shape[0]))
+        assert np.array_equal(allg, np.arange(n))
     # union of the per-rank pair lists == global pair set, each pair exactly once
     allp = np.concatenate([x["pairs"] for x in res])
     allp = allp[np.lexsort((allp[:, 1], allp[:, 0]))]
-    assert allp.shape == ref.shape
-    assert np.array_equal(allp, ref)
-
-
-_PORT = []
-
-
-def _free_port_once():
-    if not _PORT:
-        _PORT.append(_free_port())
-    return _PORT[0]
+    assert allp.shape == ref["iap"].shape
+    assert np.array_equal(allp, ref["iap"].astype(np.int64))
+    # pairs across the periodic face between rank 0 and rank W-1 are part of it
+    nc, lay = res[0]["nc"], np.floor(r[:, 0] * (res[0]["nc"] / BOX[0])).astype(int)
+    assert np.any((lay[ref["iap"][:, 0]] == 0) & (lay[ref["iap"][:, 1]] == nc - 1))
+    gid = np.concatenate([x["gids"] for x in res])
+    for k in ("rho", "p", "vdot", "udot"):
+        full = np.empty_like(ref[k])
+        full[gid] = np.concatenate([x[k] for x in res])
+        scale = np.maximum(np.abs(ref[k]), 1e-3 * np.max(np.abs(ref[k])))
+        assert np.max(np.abs(full - ref[k]) / scale) < 1e-10, k
 
 
 def test_single_rank_decomposition_is_identity():
@@ -125,7 +177,7 @@ def test_single_rank_decomposition_is_identity():
 # SlabStepper: improved Euler + periodic box + thermostat over two ranks against the same arithmetic on one process.
 # The derivative evaluation is a stand-in (every rank gathers the whole box and asks the C oracle), so that the
 # test pins the stepper's own logic: predictor / corrector bookkeeping across a migration, box, global thermostat.
-STEP_DIMS, STEP_DT, STEP_N, STEP_T = (12, 6, 6), 0.05, 3, 1.3
+STEP_DIMS, STEP_DT, STEP_N, STEP_T = (16, 6, 6), 0.05, 3, 1.3
 
 
 class _OracleSim(object):
@@ -233,18 +285,9 @@ def _one_process_steps():
 
 
 @pytest.mark.timeout(300)
-def test_slab_stepper_world2_matches_one_process():
-    world = 2
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = _free_port()
-    procs = [ctx.Process(target=_step_worker, args=(r, world, port, q)) for r in range(world)]
-    for p in procs:
-        p.start()
-    res = q.get(timeout=240)
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_stepper_matches_one_process(world):
+    res = _spawn(_step_worker, world)
     ref = _one_process_steps()
     n = ref["r"].shape[0]
     gid = np.concatenate([x["gid"] for x in res])

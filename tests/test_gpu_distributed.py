@@ -1,6 +1,8 @@
-"""GPU suite, needs >= 2 GPUs (skipped otherwise): the slab-decomposed evaluation over NCCL
-against the CPU oracle on the whole box -- global pair set bit-exact (each pair reported once),
-rho / p / vdot / udot of every particle within 1e-10."""
+"""GPU suite, needs >= 2 GPUs (skipped otherwise; world 4 and 8 need that many): the slab-decomposed
+evaluation over NCCL against the CPU oracle on the whole box -- global pair set bit-exact (each pair
+reported once), rho / p / vdot / udot of every particle within 1e-10 -- with a neighbour-capacity overflow
+forced on ONE rank (settled collectively), bit-reproducibility of a second evaluation, and SlabStepper on
+CUDA against the single-process SmoothParticleSystem.update."""
 import os
 import socket
 
@@ -10,8 +12,12 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-DIMS = (48, 16, 16)
 CUTOFF, TOL, FCUT, H = 2.0, 0.0, 5.0, 2.0
+EOS = (2.0, 0.5, 1.0)
+
+
+def _dims(world):
+    return (24 * world, 16, 16)
 
 
 def _port():
@@ -22,31 +28,52 @@ def _port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _init(rank, world, port):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    return dev
+
+
+def _rows(D, dev, r, v, t, mine, gid):
+    k = int(mine.sum())
+    one = torch.ones(k, dtype=torch.float64, device=dev)
+    return D.make_rows(torch.from_numpy(r[mine]).to(dev), torch.from_numpy(v[mine]).to(dev), one, one * H,
+                       torch.from_numpy(t[mine]).to(dev), torch.from_numpy(gid[mine]).to(dev))
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    dev = _init(rank, world, port)
     try:
         from oracle import oracle as O
         from pyticles_b200 import distributed as D
-        r, v, box = O.lattice_workload(*DIMS, seed=41, jitter=0.25)
+        r, v, box = O.lattice_workload(*_dims(world), seed=41, jitter=0.25)
         n = r.shape[0]
         gid = np.arange(n)
-        mine = (gid // (n // world)) == rank
-        k = int(mine.sum())
-        one = torch.ones(k, dtype=torch.float64, device=dev)
-        rows = D.make_rows(torch.from_numpy(r[mine]).to(dev), torch.from_numpy(v[mine]).to(dev), one, one * H, one,
-                           torch.from_numpy(gid[mine]).to(dev))
-        ev = D.SlabSphEvaluator(rows, box, CUTOFF, TOL, FCUT, (2.0, 0.5, 1.0), n, dev)
+        mine = gid % world == rank                                # not spatial: the constructor migrates
+        ev = D.SlabSphEvaluator(_rows(D, dev, r, v, np.ones(n), mine, gid), box, CUTOFF, TOL, FCUT, EOS, n, dev)
+        if rank == world - 1:
+            ev.be.user_max_nbrs = 12                              # this rank alone overflows its rows
+        k0 = ev.be.user_max_nbrs
         ev.evaluate()
-        ev.check()
-        res = {"gid": ev.own_gid.cpu().numpy(),
-               "pairs": ev.local_pairs_global_ids().cpu().numpy()}
+        ev.check()                                                # every rank re-evaluates together
+        res = {"gid": ev.own_gid.cpu().numpy(), "K": ev.max_nbrs, "K0": k0, "ghosts": ev.ghosts,
+               "pairs": ev.local_pairs_global_ids().cpu().numpy(), "ppp": ev.pairs_per_particle()}
         for kx in ("rho", "p", "vdot", "udot"):
             res[kx] = ev.result[kx].cpu().numpy()
+        ev.evaluate()
+        ev.check()
+        res["same_bits"] = all(np.array_equal(res[kx], ev.result[kx].cpu().numpy()) for kx in ("rho", "p", "vdot", "udot"))
+        # a halo buffer that is too small is grown collectively as well
+        ev._set_halo_cap(64)
+        ev.evaluate()
+        ev.check()
+        res["halo_regrown"] = ev.halo_cap > 64 and all(
+            np.array_equal(res[kx], ev.result[kx].cpu().numpy()) for kx in ("rho", "p", "vdot", "udot"))
         out = [None] * world
         dist.all_gather_object(out, res)
         if rank == 0:
@@ -55,34 +82,135 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.timeout(600)
-def test_two_gpu_slab_evaluation_matches_oracle():
+def _spawn(target, world, timeout=500):
+    import queue
+    import time
     import torch.multiprocessing as mp
-    from oracle import c_oracle as C
-    from oracle import oracle as O
-    world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=target, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = q.get(timeout=500)
+    res, t0 = None, time.time()
+    try:
+        while res is None:
+            try:
+                res = q.get(timeout=2.0)
+            except queue.Empty:
+                if time.time() - t0 > timeout or any(p.exitcode not in (None, 0) for p in procs):
+                    raise AssertionError("a rank failed or timed out")
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
     for p in procs:
-        p.join(timeout=60)
         assert p.exitcode == 0
-    r, v, box = O.lattice_workload(*DIMS, seed=41, jitter=0.25)
+    return res
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_evaluation_matches_oracle(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    from oracle import c_oracle as C
+    from oracle import oracle as O
+    res = _spawn(_worker, world)
+    r, v, box = O.lattice_workload(*_dims(world), seed=41, jitter=0.25)
     n = r.shape[0]
     ref = C.sph_step(r, v, np.ones(n), np.full(n, H), np.ones(n), np.array(box), CUTOFF, TOL, FCUT)
     pairs = np.concatenate([x["pairs"] for x in res])
     pairs = pairs[np.lexsort((pairs[:, 1], pairs[:, 0]))]
     assert np.array_equal(pairs, ref["iap"].astype(np.int64))
+    assert abs(res[0]["ppp"] - ref["iap"].shape[0] / n) < 1e-12
     gid = np.concatenate([x["gid"] for x in res])
     assert np.array_equal(np.sort(gid), np.arange(n))
+    # the overflow forced on the last rank grew every rank's capacity
+    assert res[-1]["K0"] == 12 and all(x["K"] == res[0]["K"] and x["K"] > 12 for x in res)
+    assert all(x["same_bits"] and x["halo_regrown"] for x in res)
+    assert all(min(x["ghosts"]) > 0 for x in res)
     for k in ("rho", "p", "vdot", "udot"):
         got = np.concatenate([x[k] for x in res])
         full = np.empty_like(ref[k])
         full[gid] = got
         scale = np.maximum(np.abs(ref[k]), 1e-3 * np.max(np.abs(ref[k])))
         assert np.max(np.abs(full - ref[k]) / scale) < 1e-10, k
+
+
+# ------------------------------------------------------------------ time stepping over the slabs
+STEP_DT, STEP_N, STEP_T, STEP_TOL = 0.02, 3, 1.2, 1.0
+
+
+def _step_inputs(world):
+    from oracle import oracle as O
+    r, v, box = O.lattice_workload(12 * world, 12, 12, seed=43, jitter=0.25, vmax=3.0)     # fast: some change rank
+    t = 1.0 + 0.2 * np.random.default_rng(3).random(r.shape[0])
+    return r, v, box, t
+
+
+def _step_worker(rank, world, port, q):
+    import torch.distributed as dist
+    dev = _init(rank, world, port)
+    try:
+        from pyticles_b200 import distributed as D
+        r, v, box, t = _step_inputs(world)
+        n = r.shape[0]
+        gid = np.arange(n)
+        mine = gid % world == rank
+        sim = D.SlabSphEvaluator(_rows(D, dev, r, v, t, mine, gid), box, CUTOFF, STEP_TOL, FCUT, EOS, n, dev)
+        st = D.SlabStepper(sim, box_kind="periodic", thermostat_temp=STEP_T, eos=EOS)
+        moved = 0
+        for _ in range(STEP_N):
+            before = sim.own_gid.clone()
+            st.step(STEP_DT)
+            moved += sim.n_owned - int(torch.isin(sim.own_gid, before).sum())
+        no = sim.n_owned
+        res = {"gid": sim.own_gid.cpu().numpy(), "moved": moved}
+        for k in ("r", "v", "t", "u", "rho", "p"):
+            res[k] = sim.S[k][:no].cpu().numpy()
+        out = [None] * world
+        dist.all_gather_object(out, res)
+        if rank == 0:
+            q.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_stepper_on_cuda_matches_single_process_update(world):
+    """distributed.SlabStepper over NCCL against SmoothParticleSystem.update (improved Euler, PeriodicBox, scaling
+    thermostat: particles.py:450-494) on one GPU.  The Verlet tolerance keeps the list of the single-process run,
+    which is built once per step, a superset at the second stage too."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    from pyticles_b200 import box as pbox
+    from pyticles_b200 import forces, neighbour_list, particles
+    res = _spawn(_step_worker, world)
+    r, v, box, t = _step_inputs(world)
+    n = r.shape[0]
+    p = particles.SmoothParticleSystem(n, d=3, maxn=n, xmax=box[0], ymax=box[1], zmax=box[2], hshort=H,
+                                       thermostat=True, thermostat_temp=STEP_T, integrator="ieuler",
+                                       simbox=pbox.PeriodicBox(xmax=box[0], ymax=box[1], zmax=box[2]), device="cuda:0")
+    p.r[0:n, :] = r
+    p.v[0:n, :] = v
+    p.t[0:n] = t
+    nl = neighbour_list.VerletList(p, cutoff=CUTOFF, tolerance=STEP_TOL)
+    p.nlists.append(nl)
+    p.nl_default = nl
+    p.forces.append(forces.SpamForce(p, nl, cutoff=FCUT))
+    for _ in range(STEP_N):
+        nl.rebuild_list = True
+        p.update(STEP_DT)
+    gid = np.concatenate([x["gid"] for x in res])
+    assert np.array_equal(np.sort(gid), np.arange(n))
+    assert sum(x["moved"] for x in res) > 0
+    for k in ("r", "v", "t", "u", "rho", "p"):
+        got = np.concatenate([x[k] for x in res])
+        full = np.empty_like(got)
+        full[gid] = got
+        ref = getattr(p, k).cpu().numpy()[:n]
+        scale = np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))
+        assert np.max(np.abs(full - ref) / scale) < 1e-9, k

@@ -92,6 +92,9 @@ def test_golden_reference_vectors(golden_dir, name):
     ((24, 24, 24), 2.0, 1.0, 0.45),      # heavy jitter, default Verlet tolerance
     ((128, 128, 1), 2.0, 0.0, 0.1),      # C2-like sheet in a deep box (coarsened z cells)
     ((40, 9, 5), 2.5, 0.5, 0.3),         # anisotropic, 2 cells across z
+    ((96, 96, 96), 2.0, 0.0, 0.1),       # 47 cell layers = 6 Morton blocks per dimension: interior block faces,
+                                         # multiply-high block-coordinate division (bench grid: 16 per dimension)
+    ((104, 72, 56), 2.0, 1.0, 0.3),      # 46 x 32 x 25 layers = 6 x 4 x 4 blocks, default Verlet tolerance
 ])
 def test_lattice_against_c_oracle(shape, cutoff, tol, jitter):
     r, v, box = O.lattice_workload(*shape, seed=11, jitter=jitter)
