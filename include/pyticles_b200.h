@@ -126,7 +126,9 @@ typedef struct sph_buffers {
                                global id) inside a cell instead of by their arrival slot, so results do not
                                depend on the order in which the neighbour rank packed them */
     int32_t n_owned;        /* > 0: original indices >= n_owned are ghosts -- binned and listed as neighbours of
-                               owned particles, but no rows, densities or forces are computed FOR them */
+                               owned particles, but no rows, densities or forces are computed FOR them.  On a grid
+                               restricted by sph_grid_restrict_x the ghosts are the particles of the first and the
+                               last local x layer; anything else raises SPH_F_OUT_OF_SLAB */
     int32_t reserved0;
 } sph_buffers;
 
@@ -186,8 +188,11 @@ int sph_nlist_build(const sph_grid *grid, const sph_buffers *buf, void *stream);
  * f_properties.spam_properties (f_properties.py:16-147), c_properties.pyx:83-211.
  * Reads t and writes rho, p, pco, u, t in ORIGINAL particle order (d_t is in/out, as p.t
  * is in the reference) and leaves press/rho^2 in vel4[.,3] for sph_force.
- * `use_hlr` != 0: long-range density only (rho_lr with h = hlr, no EOS;
+ * `use_hlr` == 1: long-range density only (rho_lr with h = hlr, no EOS;
  * f_properties.py:102-107) -- d_p..d_t may then be NULL.
+ * `use_hlr` == 2: density + EOS in SpamComplete's direction (spam_complete_force.py:134,151-152): d_u is
+ * the integrated internal energy (read, not written), T = max((u + a rho) / kb, 0) is written to d_t and
+ * the pressures follow from that T.
  * `list_fresh` != 0 promises positions are those the cell list was built from. */
 int sph_density_eos(const sph_grid *grid, const sph_buffers *buf, const sph_eos *eos,
                     const double *d_h_orig, int h_uniform, int list_fresh, int use_hlr,
@@ -239,6 +244,25 @@ int sph_gradv(const sph_grid *grid, const sph_buffers *buf, const double *d_rho,
 int sph_viscous_force(const sph_grid *grid, const sph_buffers *buf, const double *d_gradv, const double *d_rho,
                       double eta, double zeta, const double *d_h_orig, int h_uniform, int list_fresh,
                       double fcutoff, double *d_aux8, double *d_vdot, double *d_udot, void *stream);
+
+/* The remaining terms of SpamComplete -- `cgrad` (density-gradient / capillary coefficient), `sigma`, `rcoef`
+ * (repulsive core size and strength) and the heat-flux output `jq` (spam_complete_force.py:28-31,52-54,113-115,
+ * 158-183).  BUILDER-DEFINED like the viscous term: their arithmetic is in the absent Fortran routine.
+ *   sph_gradient      out_i = sum_j wgt_j (f_j - [subtract_self] f_i) grad_i W_ij, grad_i W_ij = -dW_ij/d(r_j - r_i);
+ *                     d_f == NULL means f = 1.  (f = 1, wgt = m: density gradient; f = T, wgt = m / rho: grad T.)
+ *   sph_stress_force  the pair force of sph_viscous_force for ANY symmetric stress tensor S[n,3,3] (original order):
+ *                     a = (S_i / rho_i^2 + S_j / rho_j^2) . dW_ij.  SpamComplete feeds it the gradient part of the
+ *                     Korteweg tensor, cgrad (g (x) g - |g|^2 I / 2) with g = grad rho_lr, on the long smoothing length.
+ *   sph_core_force    phi(r) = rcoef (1 - r^2 / sigma^2)^4 per unit mass for r < sigma (Hoover's SPAM core):
+ *                     a = -(8 rcoef / sigma^2) (1 - r^2 / sigma^2)^3 (r_j - r_i), +a to i, -a to j.
+ * All three ACCUMULATE (forces) or overwrite (gradient) in original order; aux4 / aux8 as above. */
+int sph_gradient(const sph_grid *grid, const sph_buffers *buf, const double *d_f, const double *d_wgt, int subtract_self,
+                 const double *d_h_orig, int h_uniform, int list_fresh, double *d_aux4, double *d_out, void *stream);
+int sph_stress_force(const sph_grid *grid, const sph_buffers *buf, const double *d_stress, const double *d_rho,
+                     const double *d_h_orig, int h_uniform, int list_fresh, double fcutoff, double *d_aux8,
+                     double *d_vdot, double *d_udot, void *stream);
+int sph_core_force(const sph_grid *grid, const sph_buffers *buf, double sigma, double rcoef, int list_fresh,
+                   double *d_vdot, double *d_udot, void *stream);
 
 /* ------------------------------------------------------------------ pair-list API surface */
 

@@ -122,6 +122,10 @@ SIGNATURES = {
     "sph_gradv": (ctypes.c_int, [_gp, _bp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
     "sph_viscous_force": (ctypes.c_int, [_gp, _bp, _vp, _vp, _dbl, _dbl, _vp, ctypes.c_int, ctypes.c_int, _dbl,
                                          _vp, _vp, _vp, _vp]),
+    "sph_gradient": (ctypes.c_int, [_gp, _bp, _vp, _vp, ctypes.c_int, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
+    "sph_stress_force": (ctypes.c_int, [_gp, _bp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _dbl, _vp, _vp, _vp,
+                                        _vp]),
+    "sph_core_force": (ctypes.c_int, [_gp, _bp, _dbl, _dbl, ctypes.c_int, _vp, _vp, _vp]),
     "sph_pairs_count": (ctypes.c_int, [_bp, _vp, _vp]),
     "sph_pairs_fill": (ctypes.c_int, [_bp, _vp, _vp, _i64, _vp]),
     "sph_exclusive_scan_u32": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp]),

@@ -157,11 +157,14 @@ class NeighbourBackend(object):
             self.fresh = False
         self.press_ready = False
 
-    def density_eos(self, eos, h, h_uniform, rho, p, pco, u, t, long_range=False):
+    def density_eos(self, eos, h, h_uniform, rho, p, pco, u, t, long_range=False, from_energy=False):
+        """`long_range`: rho only, with this h (the hlr density).  `from_energy`: SpamComplete's direction --
+        u is read, T = max((u + a rho) / kb, 0) is written to t and the pressures follow from it."""
         e = SphEos(float(eos[0]), float(eos[1]), float(eos[2]))
+        mode = 1 if long_range else (2 if from_energy else 0)
         check(self.lib.sph_density_eos(ctypes.byref(self.grid), ctypes.byref(self.buf), ctypes.byref(e),
                                        _ptr(_f64(h, "h")), int(bool(h_uniform)), int(self.fresh),
-                                       int(bool(long_range)), _ptr(rho), _ptr(p), _ptr(pco), _ptr(u), _ptr(t),
+                                       mode, _ptr(rho), _ptr(p), _ptr(pco), _ptr(u), _ptr(t),
                                        _stream()), "sph_density_eos")
         self.press_ready = not long_range
 
@@ -205,6 +208,28 @@ class NeighbourBackend(object):
                                          int(bool(h_uniform)), int(self.fresh), float(fcutoff), _ptr(aux8),
                                          _ptr(_f64(vdot, "vdot")), _ptr(_f64(udot, "udot")), _stream()),
               "sph_viscous_force")
+
+    def gradient(self, f, wgt, subtract_self, h, h_uniform, out):
+        """sph_gradient: out_i = sum_j wgt_j (f_j - [subtract_self] f_i) grad_i W_ij (f None: f = 1); builder-defined."""
+        aux4 = self._alloc("aux4", 4 * self.n, torch.float64)
+        check(self.lib.sph_gradient(ctypes.byref(self.grid), ctypes.byref(self.buf),
+                                    _ptr(_f64(f, "f")) if f is not None else ctypes.c_void_p(0), _ptr(_f64(wgt, "wgt")),
+                                    int(bool(subtract_self)), _ptr(_f64(h, "h")), int(bool(h_uniform)), int(self.fresh),
+                                    _ptr(aux4), _ptr(_f64(out, "out")), _stream()), "sph_gradient")
+
+    def stress_force(self, stress, rho, h, h_uniform, fcutoff, vdot, udot):
+        """sph_stress_force: tensor pair force of a symmetric stress [n,3,3], accumulated into vdot / udot."""
+        aux8 = self._alloc("aux8", 8 * self.n, torch.float64)
+        check(self.lib.sph_stress_force(ctypes.byref(self.grid), ctypes.byref(self.buf), _ptr(_f64(stress, "stress")),
+                                        _ptr(_f64(rho, "rho")), _ptr(_f64(h, "h")), int(bool(h_uniform)),
+                                        int(self.fresh), float(fcutoff), _ptr(aux8), _ptr(_f64(vdot, "vdot")),
+                                        _ptr(_f64(udot, "udot")), _stream()), "sph_stress_force")
+
+    def core_force(self, sigma, rcoef, vdot, udot):
+        """sph_core_force: the repulsive core of SpamComplete (sigma, rcoef), accumulated into vdot / udot."""
+        check(self.lib.sph_core_force(ctypes.byref(self.grid), ctypes.byref(self.buf), float(sigma), float(rcoef),
+                                      int(self.fresh), _ptr(_f64(vdot, "vdot")), _ptr(_f64(udot, "udot")), _stream()),
+              "sph_core_force")
 
     def compress(self):
         check(self.lib.sph_compress(ctypes.byref(self.grid), ctypes.byref(self.buf), _stream()), "sph_compress")

@@ -77,8 +77,8 @@ struct HaloLists {
 
 __global__ void __launch_bounds__(kBlock)
 bin_kernel(const __grid_constant__ sph_grid g, const double *__restrict__ r, int first, int count,
-           const int32_t *__restrict__ n_valid, uint32_t *__restrict__ cell_count, uint32_t *__restrict__ code,
-           uint32_t *__restrict__ rank, sph_status *__restrict__ status, HaloLists hl)
+           const int32_t *__restrict__ n_valid, int n_owned, uint32_t *__restrict__ cell_count,
+           uint32_t *__restrict__ code, uint32_t *__restrict__ rank, sph_status *__restrict__ status, HaloLists hl)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = first + k;
@@ -95,6 +95,9 @@ bin_kernel(const __grid_constant__ sph_grid g, const double *__restrict__ r, int
             rank[i] = atomicAdd(cell_count + c.code, 1u);
             left = c.cx == 1;
             right = c.cx == g.ncl[0] - 2;
+            // slab decomposition: owned particles live in the inner layers, ghosts in the two outer ones
+            if (n_owned > 0 && !g.wrap[0] && ((c.cx == 0 || c.cx == g.ncl[0] - 1) != (i >= n_owned)))
+                flags |= SPH_F_OUT_OF_SLAB;
         }
     }
     flags = __reduce_or_sync(0xffffffffu, flags);
@@ -604,15 +607,25 @@ density_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
     // properties.py:76-77: every particle starts from W(0; h[0]) -- not m_i * W(0; h_i)
     const double rho = qn + sum;
     rho_out[orig] = rho;
-    if (long_range) return;
-    const double t = t_io[orig];
-    const double p = (rho * eos.kbdash * t) / (1 - rho * eos.bdash);        // properties.py:41
+    if (long_range == 1) return;
+    double t_eos, t_new;
+    if (long_range == 2) {
+        // SpamComplete: u is the integrated state and T follows from it (spam_complete_force.py:134,151-152:
+        // calc_vdw_temp, then T[T < 0] = 0); u is left alone
+        t_new = (u_out[orig] + eos.adash * rho) / eos.kbdash;               // properties.py:49
+        if (t_new < 0.0) t_new = 0.0;
+        t_eos = t_new;
+    } else {
+        t_eos = t_io[orig];
+        const double u = t_eos * eos.kbdash - eos.adash * rho;              // properties.py:46,119
+        u_out[orig] = u;
+        t_new = (u + eos.adash * rho) / eos.kbdash;                         // properties.py:49,120
+    }
+    const double p = (rho * eos.kbdash * t_eos) / (1 - rho * eos.bdash);    // properties.py:41
     const double pco = -eos.adash * rho * rho;
-    const double u = t * eos.kbdash - eos.adash * rho;                      // properties.py:46,119
     p_out[orig] = p;
     pco_out[orig] = pco;
-    u_out[orig] = u;
-    t_io[orig] = (u + eos.adash * rho) / eos.kbdash;                        // properties.py:49,120
+    t_io[orig] = t_new;
     vel4[4 * (size_t)a + 3] = p / (rho * rho);                              // forces.py:353 operand
 }
 
@@ -1390,8 +1403,8 @@ int sph_cells_begin(const sph_grid *g, const sph_buffers *b, const double *d_r, 
     cudaMemsetAsync(b->cell_count, 0, sizeof(uint32_t) * ((size_t)g->ncode + 1), s);
     const HaloLists hl = {d_idx_left, d_idx_right, (uint32_t)cap};
     if (count > 0)
-        bin_kernel<<<blocks_for(count, kBlock), kBlock, 0, s>>>(*g, d_r, first, count, b->n_valid, b->cell_count,
-                                                                b->code, b->rank, b->status, hl);
+        bin_kernel<<<blocks_for(count, kBlock), kBlock, 0, s>>>(*g, d_r, first, count, b->n_valid, b->n_owned,
+                                                                b->cell_count, b->code, b->rank, b->status, hl);
     return launch_status();
 }
 
@@ -1402,7 +1415,7 @@ int sph_cells_add(const sph_grid *g, const sph_buffers *b, const double *d_r, in
     const HaloLists hl = {nullptr, nullptr, 0u};
     if (count > 0)
         bin_kernel<<<blocks_for(count, kBlock), kBlock, 0, (cudaStream_t)stream>>>(
-            *g, d_r, first, count, b->n_valid, b->cell_count, b->code, b->rank, b->status, hl);
+            *g, d_r, first, count, b->n_valid, b->n_owned, b->cell_count, b->code, b->rank, b->status, hl);
     return launch_status();
 }
 
@@ -1486,7 +1499,7 @@ int sph_density_eos(const sph_grid *g, const sph_buffers *b, const sph_eos *eos,
                     double *d_rho, double *d_p, double *d_pco, double *d_u, double *d_t, void *stream)
 {
     if (!g || !b || !eos || !d_h_orig || !d_rho) return SPH_E_BADARG;
-    if (!use_hlr && (!d_p || !d_pco || !d_u || !d_t)) return SPH_E_BADARG;
+    if (use_hlr < 0 || use_hlr > 2 || (use_hlr != 1 && (!d_p || !d_pco || !d_u || !d_t))) return SPH_E_BADARG;
     if (b->n == 0) return SPH_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int lpp = lanes_per_particle();

@@ -247,6 +247,172 @@ viscous_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
     }
 }
 
+// ------------------------------------------------------------------ SPH gradient of a per-particle scalar
+// BUILDER-DEFINED (the reference hands grad_rho_lr and the heat flux jq to the absent Fortran routine,
+// spam_complete_force.py:113-115,158-165):
+//     out_i = sum_j wgt_j (f_j - c f_i) grad_i W_ij,   grad_i W_ij = -dW_ij/d(r_j - r_i)
+// With f = 1, c = 0, wgt = m this is the density gradient sum_j m_j grad_i W_ij; with f = T, c = 1,
+// wgt = m / rho it is the usual difference form of grad T.  aux4[a] = (f, wgt, 0, 0) of sorted particle a.
+__global__ void __launch_bounds__(kBlock)
+scalar_term_kernel(int n, const int32_t *__restrict__ perm, const double *__restrict__ f,
+                   const double *__restrict__ wgt, double *__restrict__ aux4)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const size_t o = (size_t)perm[a];
+    store4(aux4 + 4 * (size_t)a, f ? f[o] : 1.0, wgt[o], 0.0, 0.0);
+}
+
+template <bool UNIFORM_H, bool WRAP>
+__device__ __forceinline__ void gradient_row(const sph_grid &g, const double *__restrict__ pos4,
+                                             const double *__restrict__ aux4, const int32_t *__restrict__ perm,
+                                             const double *__restrict__ h_orig, const int32_t *__restrict__ row,
+                                             int count, int orig, int self, double px, double py, double pz,
+                                             double fself, double hinv, double c2, double G[3])
+{
+    int jn = count > 0 ? row[0] : self;
+    for (int k = 0; k < count; ++k) {
+        const int j = jn;
+        double bx, by, bz, bm, fj, wj, e2, e3;
+        load4(pos4 + 4 * (size_t)j, bx, by, bz, bm);
+        load4(aux4 + 4 * (size_t)j, fj, wj, e2, e3);
+        jn = k + 1 < count ? row[(size_t)(k + 1) * 32] : self;
+        const Geom q = pair_geom<UNIFORM_H, WRAP>(g, px, py, pz, bx, by, bz, perm, h_orig, orig, j, hinv, c2);
+        if (q.in) {
+            const double w = wj * (fj - fself);
+            G[0] -= w * (q.fac * q.dx);
+            G[1] -= w * (q.fac * q.dy);
+            G[2] -= w * (q.fac * q.dz);
+        }
+        (void)bm; (void)e2; (void)e3;
+    }
+}
+
+template <bool UNIFORM_H>
+__global__ void __launch_bounds__(kBlock)
+gradient_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__restrict__ pos4,
+                const double *__restrict__ aux4, const float *__restrict__ rel4, const int32_t *__restrict__ perm,
+                const int32_t *__restrict__ nbr, const int32_t *__restrict__ cnt,
+                const sph_status *__restrict__ status, const double *__restrict__ h_orig, int list_fresh,
+                int subtract_self, double *__restrict__ out)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = a < n;
+    double px = 0, py = 0, pz = 0, pm = 0, fs = 0, ws = 0, e2 = 0, e3 = 0;
+    int count = 0, orig = 0;
+    bool interior = true;
+    if (active) {
+        load4(pos4 + 4 * (size_t)a, px, py, pz, pm);
+        load4(aux4 + 4 * (size_t)a, fs, ws, e2, e3);
+        count = min(cnt[a], K);
+        orig = perm[a];
+        interior = __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w) != 0u;
+    }
+    const bool can_skip = list_fresh && !(status->flags & (SPH_F_OUT_OF_BOX | SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
+    const bool skip = __all_sync(0xffffffffu, interior) && can_skip;
+    const double h0 = h_orig[0];
+    const double hinv = 1.0 / h0, c2 = -12.0 * lucy_norm3(h0) * hinv * hinv;
+    const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
+    double G[3] = {0, 0, 0};
+    const double fself = subtract_self ? fs : 0.0;
+    if (skip) gradient_row<UNIFORM_H, false>(g, pos4, aux4, perm, h_orig, row, count, orig, a, px, py, pz, fself, hinv, c2, G);
+    else gradient_row<UNIFORM_H, true>(g, pos4, aux4, perm, h_orig, row, count, orig, a, px, py, pz, fself, hinv, c2, G);
+    (void)pm; (void)ws; (void)e2; (void)e3;
+    if (active) {
+        out[3 * (size_t)orig] = G[0];
+        out[3 * (size_t)orig + 1] = G[1];
+        out[3 * (size_t)orig + 2] = G[2];
+    }
+}
+
+// aux8[a] = S / rho^2 of sorted particle a as (xx, yy, zz, xy, xz, yz, 0, 0) for a symmetric stress S[n,3,3]
+__global__ void __launch_bounds__(kBlock)
+stress_pack_kernel(int n, const int32_t *__restrict__ perm, const double *__restrict__ stress,
+                   const double *__restrict__ rho, double *__restrict__ aux8)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const size_t o = (size_t)perm[a];
+    const double *S = stress + 9 * o;
+    const double d = rho[o], inv = 1.0 / (d * d);
+    store4(aux8 + 8 * (size_t)a, S[0] * inv, S[4] * inv, S[8] * inv, (0.5 * (S[1] + S[3])) * inv);
+    store4(aux8 + 8 * (size_t)a + 4, (0.5 * (S[2] + S[6])) * inv, (0.5 * (S[5] + S[7])) * inv, 0.0, 0.0);
+}
+
+// ------------------------------------------------------------------ repulsive core
+// BUILDER-DEFINED (SpamComplete's `sigma` = core size, `rcoef` = core strength, spam_complete_force.py:28-29,52-53,
+// arithmetic in the absent Fortran).  Pair potential per unit mass phi(r) = rcoef (1 - r^2/sigma^2)^4 for r < sigma:
+//     a = -(8 rcoef / sigma^2) (1 - r^2/sigma^2)^3 (r_j - r_i),  +a to i, -a to j (no mass factor, like the pressure
+//     force), du = a . dv / 2, udot_i += du m_j, udot_j += du m_i   (the conventions of forces.py:353-368)
+template <bool WRAP>
+__device__ __forceinline__ VAcc core_row(const sph_grid &g, const double *__restrict__ pos4,
+                                         const double *__restrict__ vel4, const int32_t *__restrict__ row, int count,
+                                         int self, double px, double py, double pz, double vx, double vy, double vz,
+                                         double inv_s2, double coef)
+{
+    VAcc f = {0.0, 0.0, 0.0, 0.0};
+    int jn = count > 0 ? row[0] : self;
+    for (int k = 0; k < count; ++k) {
+        const int j = jn;
+        double bx, by, bz, bm, wx, wy, wz, ww;
+        load4(pos4 + 4 * (size_t)j, bx, by, bz, bm);
+        load4(vel4 + 4 * (size_t)j, wx, wy, wz, ww);
+        jn = k + 1 < count ? row[(size_t)(k + 1) * 32] : self;
+        double dx = bx - px, dy = by - py, dz = bz - pz;
+        if (WRAP) {
+            dx = min_image(dx, g.box[0], g.box[0] / 2.);
+            dy = min_image(dy, g.box[1], g.box[1] / 2.);
+            dz = min_image(dz, g.box[2], g.box[2] / 2.);
+        }
+        const double s = rsq_exact(dx, dy, dz) * inv_s2;
+        if (s < 1.0) {
+            const double t = 1.0 - s;
+            const double fac = coef * (t * t * t);
+            const double gx = fac * dx, gy = fac * dy, gz = fac * dz;
+            f.ax += gx;
+            f.ay += gy;
+            f.az += gz;
+            const double dot = (gx * (wx - vx) + gy * (wy - vy)) + gz * (wz - vz);
+            f.du += (0.5 * dot) * bm;
+        }
+        (void)ww;
+    }
+    return f;
+}
+
+__global__ void __launch_bounds__(kBlock)
+core_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__restrict__ pos4,
+            const double *__restrict__ vel4, const float *__restrict__ rel4, const int32_t *__restrict__ perm,
+            const int32_t *__restrict__ nbr, const int32_t *__restrict__ cnt, const sph_status *__restrict__ status,
+            int list_fresh, double inv_s2, double coef, double *__restrict__ vdot, double *__restrict__ udot)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = a < n;
+    double px = 0, py = 0, pz = 0, pm = 0, vx = 0, vy = 0, vz = 0, vw = 0;
+    int count = 0, orig = 0;
+    bool interior = true;
+    if (active) {
+        load4(pos4 + 4 * (size_t)a, px, py, pz, pm);
+        load4(vel4 + 4 * (size_t)a, vx, vy, vz, vw);
+        count = min(cnt[a], K);
+        orig = perm[a];
+        interior = __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w) != 0u;
+    }
+    const bool can_skip = list_fresh && !(status->flags & (SPH_F_OUT_OF_BOX | SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
+    const bool skip = __all_sync(0xffffffffu, interior) && can_skip;
+    const int32_t *row = nbr + ((size_t)(a >> 5) * (size_t)K) * 32 + (a & 31);
+    VAcc f;
+    if (skip) f = core_row<false>(g, pos4, vel4, row, count, a, px, py, pz, vx, vy, vz, inv_s2, coef);
+    else f = core_row<true>(g, pos4, vel4, row, count, a, px, py, pz, vx, vy, vz, inv_s2, coef);
+    (void)pm; (void)vw;
+    if (active) {
+        vdot[3 * (size_t)orig] += f.ax;
+        vdot[3 * (size_t)orig + 1] += f.ay;
+        vdot[3 * (size_t)orig + 2] += f.az;
+        udot[orig] += f.du;
+    }
+}
+
 inline int blocks_of(int64_t n) { return (int)((n + kBlock - 1) / kBlock); }
 
 inline int status_of_launch()
@@ -296,6 +462,59 @@ int sph_viscous_force(const sph_grid *g, const sph_buffers *b, const double *d_g
         viscous_kernel<false><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, b->vel4, d_aux8, b->rel4, b->perm,
                                                     b->nbr, b->cnt, b->status, d_h_orig, list_fresh, fcutsq, d_vdot,
                                                     d_udot);
+    return status_of_launch();
+}
+
+int sph_gradient(const sph_grid *g, const sph_buffers *b, const double *d_f, const double *d_wgt, int subtract_self,
+                 const double *d_h_orig, int h_uniform, int list_fresh, double *d_aux4, double *d_out, void *stream)
+{
+    if (!g || !b || !d_wgt || !d_h_orig || !d_aux4 || !d_out) return SPH_E_BADARG;
+    if (!b->pos4 || !b->rel4 || !b->perm || !b->nbr || !b->cnt || !b->status) return SPH_E_BADARG;
+    if (b->n == 0) return SPH_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nb = blocks_of(b->n);
+    scalar_term_kernel<<<nb, kBlock, 0, s>>>(b->n, b->perm, d_f, d_wgt, d_aux4);
+    if (h_uniform)
+        gradient_kernel<true><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, d_aux4, b->rel4, b->perm, b->nbr,
+                                                    b->cnt, b->status, d_h_orig, list_fresh, subtract_self, d_out);
+    else
+        gradient_kernel<false><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, d_aux4, b->rel4, b->perm, b->nbr,
+                                                     b->cnt, b->status, d_h_orig, list_fresh, subtract_self, d_out);
+    return status_of_launch();
+}
+
+int sph_stress_force(const sph_grid *g, const sph_buffers *b, const double *d_stress, const double *d_rho,
+                     const double *d_h_orig, int h_uniform, int list_fresh, double fcutoff, double *d_aux8,
+                     double *d_vdot, double *d_udot, void *stream)
+{
+    if (!g || !b || !d_stress || !d_rho || !d_h_orig || !d_aux8 || !d_vdot || !d_udot) return SPH_E_BADARG;
+    if (!b->pos4 || !b->vel4 || !b->rel4 || !b->perm || !b->nbr || !b->cnt || !b->status) return SPH_E_BADARG;
+    if (b->n == 0) return SPH_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int nb = blocks_of(b->n);
+    const double fcutsq = fcutoff * fcutoff;                         // forces.py:36
+    stress_pack_kernel<<<nb, kBlock, 0, s>>>(b->n, b->perm, d_stress, d_rho, d_aux8);
+    if (h_uniform)
+        viscous_kernel<true><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, b->vel4, d_aux8, b->rel4, b->perm,
+                                                   b->nbr, b->cnt, b->status, d_h_orig, list_fresh, fcutsq, d_vdot,
+                                                   d_udot);
+    else
+        viscous_kernel<false><<<nb, kBlock, 0, s>>>(*g, b->n, b->max_nbrs, b->pos4, b->vel4, d_aux8, b->rel4, b->perm,
+                                                    b->nbr, b->cnt, b->status, d_h_orig, list_fresh, fcutsq, d_vdot,
+                                                    d_udot);
+    return status_of_launch();
+}
+
+int sph_core_force(const sph_grid *g, const sph_buffers *b, double sigma, double rcoef, int list_fresh, double *d_vdot,
+                   double *d_udot, void *stream)
+{
+    if (!g || !b || !d_vdot || !d_udot || !(sigma > 0.0)) return SPH_E_BADARG;
+    if (!b->pos4 || !b->vel4 || !b->rel4 || !b->perm || !b->nbr || !b->cnt || !b->status) return SPH_E_BADARG;
+    if (b->n == 0) return SPH_OK;
+    const double inv_s2 = 1.0 / (sigma * sigma);
+    core_kernel<<<blocks_of(b->n), kBlock, 0, (cudaStream_t)stream>>>(
+        *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, list_fresh, inv_s2,
+        -8.0 * rcoef * inv_s2, d_vdot, d_udot);
     return status_of_launch();
 }
 

@@ -362,31 +362,32 @@ class SlabSphEvaluator(object):
             self._events.append(ev)
         self.result = dict(rho=rho[:no], p=p[:no], pco=pco[:no], u=u[:no], vdot=vdot[:no], udot=udot[:no])
 
-    def check(self):
+    def check(self, _depth=0):
         """Sync, read the status block and settle capacity overflows COLLECTIVELY: when any rank overflowed
         (neighbour rows or halo buffers) every rank grows to the largest need and re-evaluates, so the ranks
         stay in step with each other's collectives; errors are raised on all ranks together."""
         torch.cuda.synchronize()
         st = self.be.status()
         fl = int(st.flags)
-        mine = [1 if fl & _lib.SPH_F_NBR_OVERFLOW else 0, int(st.max_count),
+        mine = [1 if fl & _lib.SPH_F_NBR_OVERFLOW else 0, int(st.max_count), int(self.be.K),
                 1 if fl & _lib.SPH_F_HALO_OVERFLOW else 0, max(int(st.halo_count[0]), int(st.halo_count[1])),
                 1 if fl & _lib.SPH_F_OUT_OF_SLAB else 0]
-        nbr_over, need_k, halo_over, need_h, lost = self.dec.all_max(mine, self.device)
+        nbr_over, need_k, have_k, halo_over, need_h, lost = self.dec.all_max(mine, self.device)
         if lost:
             raise _lib.SphError("a particle lies outside some rank's cell layers (missing migrate()?)")
         if nbr_over or halo_over:
+            if _depth >= 4:
+                raise _lib.SphError("capacity overflow not settled after %d re-evaluations" % _depth)
             if nbr_over:
-                if need_k <= self.be.K:
-                    raise _lib.SphError("inconsistent neighbour overflow status")
+                # every rank ends up with the same capacity: the largest need seen anywhere plus a margin
                 self.be.user_max_nbrs = None
-                self.be.ensure(self.be.n, K=need_k + max(4, need_k // 8))
+                self.be.ensure(self.be.n, K=max(have_k, need_k + max(4, need_k // 8)))
             if halo_over:
                 if need_h <= self.halo_cap:
                     raise _lib.SphError("inconsistent halo overflow status")
                 self._set_halo_cap(need_h + need_h // 8 + 64)
             self.evaluate()
-            return self.check()
+            return self.check(_depth + 1)
         self.ghosts = (int(st.ghost_count[0]), int(st.ghost_count[1]))
         return st
 

@@ -9,9 +9,12 @@
 `apply()` runs the CUDA force pass (sph_force) over the neighbour structure and ACCUMULATES
 into p.vdot / p.udot, so several forces stack exactly as in the reference
 (particles.py:549-550 zeroes them once per evaluation).  The acceleration carries no mass
-factor while udot does (forces.py:353-368) -- kept.  Hooke, gravity and collision forces are
-toy forces outside the SPH hot path and are not provided.
+factor while udot does (forces.py:353-368) -- kept.  Hooke and gravity forces are toy forces outside
+the SPH hot path and are not provided; FortranCollisionForce is here only because
+run_scripts/bspana.py:46 appends it next to SpamComplete.
 """
+import torch
+
 from . import properties as _properties
 
 
@@ -117,3 +120,43 @@ class SpamConduction(Force):
         p, nl = self.p, self.nl
         nl._refresh_sorted()
         nl.backend.conduction(p.jq, p.rho, p.h, _properties._h_uniform(p, p.h), p.udot)
+
+
+class FortranCollisionForce(Force):
+    """forces.py:454-473: pairs with rij^2 <= cutoff^2 get `collision.collide3d(v_i, v_j, m_i, m_j, drij, rsq)`, a
+    routine of the external Fortran module the reference does not ship.  BUILDER-DEFINED stand-in, so that the
+    reference's front end runs unchanged (run_scripts/bspana.py:46): an instantaneous elastic collision of two hard
+    spheres along their line of centres -- approaching pairs exchange the impulse 2 m_i m_j / (m_i + m_j) (dv . n) n,
+    receding pairs are left alone -- applied pair by pair in list order like the reference's Force.apply loop
+    (forces.py:38-42).  Not on the SPH hot path: it works on the exported pair list with plain tensor operations and
+    touches the few pairs inside the (small) collision cutoff only."""
+
+    def __init__(self, particles, neighbour_list, cutoff=1.0):
+        Force.__init__(self, particles, neighbour_list, cutoff=cutoff)
+
+    def apply(self):
+        nl = self.nl
+        if nl.nip == 0:
+            return
+        use = (nl.rsq[:nl.nip].as_subclass(torch.Tensor) <= self.cutoffsq).nonzero().flatten().tolist()
+        for k in use:
+            self.apply_force(k)
+
+    apply_sorted = apply
+
+    def apply_force(self, k):
+        p, nl = self.p, self.nl
+        i, j = int(nl.iap[k, 0]), int(nl.iap[k, 1])
+        d = nl.drij[k].as_subclass(torch.Tensor)
+        rr = torch.sqrt(nl.rsq[k].as_subclass(torch.Tensor))
+        if float(rr) == 0.0:
+            return
+        nhat = d / rr
+        vi, vj = p.v[i].as_subclass(torch.Tensor), p.v[j].as_subclass(torch.Tensor)
+        closing = torch.dot(vj - vi, nhat)
+        if float(closing) >= 0.0:
+            return
+        mi, mj = float(p.m[i]), float(p.m[j])
+        imp = (2.0 * mi * mj / (mi + mj)) * closing * nhat
+        p.v[i] = vi + imp / mi
+        p.v[j] = vj - imp / mj

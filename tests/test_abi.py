@@ -146,7 +146,8 @@ def test_variant_sweep_flags_exist_in_the_source():
     spec = importlib.util.spec_from_file_location("variant_sweep", os.path.join(ROOT, "tools", "variant_sweep.py"))
     vs = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(vs)
-    src = open(os.path.join(ROOT, "pyticles_b200", "csrc", "sph_kernels.cu")).read()
+    src = open(os.path.join(ROOT, "pyticles_b200", "csrc", "sph_kernels.cu")).read() + \
+        open(os.path.join(ROOT, "pyticles_b200", "csrc", "sph_tiles.cu")).read()
     assert vs.VARIANTS["default"] == []
     for name, flags in vs.VARIANTS.items():
         for f in flags:
@@ -182,3 +183,7 @@ def test_header_is_plain_c_and_links(tmp_path, lib):
     assert out.returncode == 0, out.stderr
     rc, nc, ver = out.stdout.split(None, 2)
     assert rc == "0" and int(nc) == 8 and "sm_100a" in ver
+    # one ABI version: the header's SPH_ABI_VERSION is what sph_version() reports and what the Python layer expects
+    hdr = open(os.path.join(ROOT, "include", "pyticles_b200.h")).read()
+    abi = int(re.search(r"#define SPH_ABI_VERSION (\d+)", hdr).group(1))
+    assert ("abi %d" % abi) in ver and _lib.SPH_ABI_VERSION == abi

@@ -78,11 +78,21 @@ def _worker(rank, world, port, q):
         dist.all_gather_object(out, res)
         if rank == 0:
             q.put(out)
+    except BaseException:
+        _die()
     finally:
         dist.destroy_process_group()
 
 
-def _spawn(target, world, timeout=500):
+def _die():
+    """A failed rank must not wait for its peers in destroy_process_group: report and leave at once, so that the
+    parent sees the exit code and stops the other ranks."""
+    import traceback
+    traceback.print_exc()
+    os._exit(1)
+
+
+def _spawn(target, world, timeout=240):
     import queue
     import time
     import torch.multiprocessing as mp
@@ -99,10 +109,13 @@ def _spawn(target, world, timeout=500):
                 res = q.get(timeout=2.0)
             except queue.Empty:
                 if time.time() - t0 > timeout or any(p.exitcode not in (None, 0) for p in procs):
+                    for p in procs:
+                        if p.is_alive():
+                            p.kill()
                     raise AssertionError("a rank failed or timed out")
     finally:
         for p in procs:
-            p.join(timeout=60)
+            p.join(timeout=30)
             if p.is_alive():
                 p.kill()
     for p in procs:
@@ -174,6 +187,8 @@ def _step_worker(rank, world, port, q):
         dist.all_gather_object(out, res)
         if rank == 0:
             q.put(out)
+    except BaseException:
+        _die()
     finally:
         dist.destroy_process_group()
 

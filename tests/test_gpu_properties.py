@@ -114,13 +114,14 @@ def test_bench_emits_contract_line():
 
 
 def test_bspana_style_front_end_runs(tmp_path):
-    """run_scripts/bspana.py usage contract on this backend: build, properties,
-    update loop with thermostat, list compression / rebuild, trajectory output."""
+    """The text of run_scripts/bspana.py:38-62 with only the import lines changed (examples/bspana.py):
+    SpamComplete with its DEFAULT arguments (cgrad = 1, eta = 1, zeta = 0.1) next to the collision force, build,
+    properties, update loop with thermostat, trajectory output."""
     env = dict(os.environ, PYTHONPATH=ROOT)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "bspana.py"), "12", "8"], cwd=str(tmp_path),
                          env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
-    assert "Completed 12 steps" in out.stdout and "nan" not in out.stdout
+    assert "Completed 11 steps" in out.stdout and "nan" not in out.stdout          # the script prints the last index
     from scipy.io import netcdf_file
     f = netcdf_file(str(tmp_path / "output.nc"), "r", mmap=False)
     assert f.variables["position"].shape == (2, 512, 3)

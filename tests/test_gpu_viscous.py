@@ -130,8 +130,9 @@ def test_viscous_force_is_pairwise_antisymmetric_and_dissipates():
 
 
 def test_spam_complete_with_viscosity():
-    """SpamComplete(eta, zeta) = its pinned pressure part (test_gpu_parity) + the viscous part above;
-    P = (p + pco) I + pi.  The capillary / core terms stay refused."""
+    """SpamComplete(eta, zeta) = its pinned pressure part + the viscous part above; P = (p + pco) I + pi.  The
+    class takes T from the integrated internal energy (spam_complete_force.py:134,151-152), so u is set to the
+    vdW energy of the test temperature first -- what spam_properties leaves behind in the reference's scripts."""
     from pyticles_b200 import neighbour_list, spam_complete_force
     r, v, m, h, t, box = _system((10, 10, 10), seed=57)
     n = r.shape[0]
@@ -140,19 +141,18 @@ def test_spam_complete_with_viscosity():
     nl = neighbour_list.VerletList(p, cutoff=3.0, tolerance=0.0)
     nl.build()
     nl.separations()
+    pr, g, pi, vd, ud, _ = _reference(r, v, m, h, t, box, 0.7, 0.3, cutoff=3.0, fcut=10.0)
+    p.u[0:n] = t * 1.0 - 2.0 * pr["rho"]                               # properties.py:46
     f0 = spam_complete_force.SpamComplete(p, nl, cgrad=0.0, eta=0.0, zeta=0.0, cutoff=10.0)
     f0.apply()
     base_v, base_u = _np(p.vdot)[:n].copy(), _np(p.udot)[:n].copy()
     f1 = spam_complete_force.SpamComplete(p, nl, cgrad=0.0, eta=0.7, zeta=0.3, cutoff=10.0)
     f1.apply()
-    pr, g, pi, vd, ud, _ = _reference(r, v, m, h, t, box, 0.7, 0.3, cutoff=3.0, fcut=10.0)
     assert rel_err(_np(p.vdot)[:n] - base_v, vd) < 1e-9
     assert rel_err(_np(p.udot)[:n] - base_u, ud) < 1e-9
     P = _np(p.P)[:n]
     want = (_np(p.p)[:n] + _np(p.pco)[:n])[:, None, None] * np.eye(3) + pi
     assert rel_err(P, want) < RTOL
-    with pytest.raises(NotImplementedError):
-        spam_complete_force.SpamComplete(p, nl).apply()               # default cgrad = 1.0
 
 
 def test_nanobox_quench_example_runs(capsys):
