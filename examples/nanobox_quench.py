@@ -5,7 +5,13 @@ lengths, the SpamComplete force with cgrad = eta = zeta = 0 as the reference scr
 periodic box, thermostat.  The reference drives `p.update(dt)` from a pyglet clock and draws; this one
 prints.  The only change to the set-up statements is where the modules are imported from.
 
-    python examples/nanobox_quench.py [steps] [side]
+    python examples/nanobox_quench.py [steps] [side] [dt]
+
+The force arithmetic that is pinned here is the one of the reference's Python twins: the acceleration carries no mass
+factor (forces.py:353-368) and the self density is W(0) whatever the mass (properties.py:76-77).  With the script's
+particle mass of 0.1386 the surface particles of the lattice block then start with accelerations of 1.5e6, and the
+script's dt = 0.01 (kept as the default) throws them across the box in one step -- the reference's Fortran routine,
+which is not available, presumably weights by mass.  Pass a smaller dt (1e-4) for a run that stays physical.
 """
 import os
 import sys
@@ -23,7 +29,7 @@ SIDE = (S, S, S)
 SPACING = 0.5
 XMAX = YMAX = ZMAX = 8 * S / 10.0          # nanobox_quench.py:59-61 for SIDE = (10, 10, 10)
 VMAX = 0.0
-dt = 0.01
+dt = float(sys.argv[3]) if len(sys.argv) > 3 else 0.01          # nanobox_quench.py:64
 NP = SIDE[0] * SIDE[1] * SIDE[2]
 TEMPERATURE = 0.8
 HLONG = 3.0

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = [os.path.join(HERE, "csrc", "sph_kernels.cu"), os.path.join(HERE, "csrc", "sph_tiles.cu"),
-       os.path.join(HERE, "csrc", "sph_viscous.cu")]
+       os.path.join(HERE, "csrc", "sph_tiles_mma.cu"), os.path.join(HERE, "csrc", "sph_viscous.cu")]
 HDR = [os.path.join(ROOT, "include", "pyticles_b200.h"), os.path.join(HERE, "csrc", "sph_device.cuh"),
        os.path.join(HERE, "csrc", "sph_tiles.cuh")]
 OUT = os.path.join(HERE, "libpyticles_b200.so")

@@ -1484,11 +1484,19 @@ int sph_nlist_build(const sph_grid *g, const sph_buffers *b, void *stream)
     if (b->max_nbrs <= 0) return SPH_E_BADARG;
     if (b->n == 0) return SPH_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    // the cell-group kernel first; the general kernel behind it returns at once unless that one gave up
-    const bool tiles = sph_tiles::eligible(g, b);
+    // the cell-group kernel first; the general kernel behind it returns at once unless that one gave up.
+    // SPH_TILES in the environment: 0 general kernel only, 1 (default) scalar cell-group kernel, 2 its tensor-core
+    // pre-filter variant (tests, A/B timing)
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("SPH_TILES");
+        mode = e ? atoi(e) : 1;
+    }
+    const bool mma = mode == 2 && sph_tiles_mma::eligible(g, b);
+    const bool tiles = mma || (mode != 0 && sph_tiles::eligible(g, b));
     if (tiles) {
         flags_clear_kernel<<<1, 1, 0, s>>>(b->status, SPH_F_TILE_FALLBACK);
-        const int rc = sph_tiles::launch_list(g, b, s);
+        const int rc = mma ? sph_tiles_mma::launch_list(g, b, s) : sph_tiles::launch_list(g, b, s);
         if (rc != SPH_OK) return rc;
     }
     return nlist_general(g, b, tiles ? 1 : 0, s);

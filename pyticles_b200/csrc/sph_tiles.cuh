@@ -21,4 +21,10 @@ int launch_list(const sph_grid *g, const sph_buffers *b, cudaStream_t s);
 
 }  // namespace sph_tiles
 
+// Tensor-core pre-filter variant of the same pass (sph_tiles_mma.cu; SPH_TILES=2 selects it): same contract.
+namespace sph_tiles_mma {
+bool eligible(const sph_grid *g, const sph_buffers *b);
+int launch_list(const sph_grid *g, const sph_buffers *b, cudaStream_t s);
+}  // namespace sph_tiles_mma
+
 #endif  // SPH_TILES_CUH

@@ -47,6 +47,10 @@ class SpamComplete(Force):
                  cgrad=1.0, eta=1.0, zeta=0.1, kernel_type=2, cutoff=5.0):
         Force.__init__(self, particles, neighbour_list, cutoff=cutoff)
         self.adash, self.bdash, self.kbdash = adash, bdash, kbdash
+        # the reference sets the equation-of-state constants of the (module-global) Fortran eos here
+        # (spam_complete_force.py:49-51: feos.eos.adash = adash ...), which is what spam_properties and the
+        # thermostat's get_vdw_u then use; the `properties` module constants play that part
+        properties.ADASH, properties.BDASH, properties.KBDASH = adash, bdash, kbdash
         self.sigma, self.rcoef, self.cgrad = sigma, rcoef, cgrad
         self.eta, self.zeta = eta, zeta
         self.kernel_type = 2                                  # spam_complete_force.py:59

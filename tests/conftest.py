@@ -31,3 +31,13 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(autouse=True)
+def _restore_eos_constants():
+    """SpamComplete sets the module-global equation-of-state constants, as the reference does with the Fortran eos
+    module (spam_complete_force.py:49-51); tests must not leak them into each other."""
+    from pyticles_b200 import properties
+    saved = (properties.ADASH, properties.BDASH, properties.KBDASH)
+    yield
+    properties.ADASH, properties.BDASH, properties.KBDASH = saved

@@ -122,7 +122,7 @@ def test_spam_complete_against_its_statement(kw):
     n = r.shape[0]
     p, nl = _gpu(r, v, m, h, hlr, t, box)
     rng = np.random.default_rng(2)
-    u = rng.uniform(-1.5, 0.5, n)                                        # some give T < 0 before the clamp
+    u = rng.uniform(-3.5, 0.5, n)                                        # some give T < 0 before the clamp
     p.u[0:n] = u
     thermalk = kw.pop("thermalk", 0.0)
     f = spam_complete_force.SpamComplete(p, nl, cutoff=10.0, **kw)

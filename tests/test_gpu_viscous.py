@@ -164,7 +164,7 @@ def test_nanobox_quench_example_runs(capsys):
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "nanobox_quench.py")
     spec = importlib.util.spec_from_file_location("nanobox_quench_example", path)
     argv = sys.argv
-    sys.argv = [path, "12", "8"]
+    sys.argv = [path, "12", "8", "1e-4"]          # see the example's docstring for the time step
     try:
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)

@@ -19,8 +19,8 @@ __device__ __forceinline__ void mma16816(float &d0, float &d1, float &d2, float 
 template <int MODE>
 __global__ void __launch_bounds__(256) probe(int iters, const uint32_t *__restrict__ in, uint32_t *__restrict__ out)
 {
-    __shared__ __align__(128) uint32_t A[64 * 8 * 4];          // 64 tiles of 16 x 16 halves (512 B each)
-    for (int i = threadIdx.x; i < 64 * 8 * 4; i += blockDim.x) A[i] = in[i & 1023];
+    __shared__ __align__(128) uint32_t A[64 * 128];            // 64 tiles of 16 x 16 halves (512 B each)
+    for (int i = threadIdx.x; i < 64 * 128; i += blockDim.x) A[i] = in[i & 1023];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     uint32_t b0 = in[lane], b1 = in[lane + 32];

@@ -48,8 +48,7 @@ VARIANTS = {
     "w_f_ahead4": _v(W, SPH_IDX_AHEAD_F=4),
     "w_f_r64": _v(W, SPH_FORCE_MINB=8),
     # round 2: the cell-group neighbour kernel (csrc/sph_tiles.cu)
-    "t_b4": ["-DSPH_TILE_BLOCKS=4"],
-    "t_b6": ["-DSPH_TILE_BLOCKS=6"],
+    "t_b4": ["-DSPH_TILE_BLOCKS=4"],      # 4 blocks per SM: 64 registers, no spills
 }
 # The other rows of the r1f sweep tables (noalloc, keep, *_smq, *_maxl1, w_f_pipe_r80, w_stride8, w_pairload, w_intra)
 # were variants whose code was removed after they lost; they can be rebuilt from commit dac84c7.
