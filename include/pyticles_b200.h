@@ -161,7 +161,8 @@ int sph_cells_build(const sph_grid *grid, const sph_buffers *buf, const double *
  * arrive, and that pass also lists the particles of the two boundary cell layers (local x layers 1 and
  * ncl[0] - 2: sph_grid_restrict_x keeps one ghost layer on each side) -- the ghosts the x-neighbours need --
  * at no extra pass over the positions.
- *   begin   zeroes the cell counters and bins particles [first, first + count); d_idx_left / d_idx_right
+ *   begin   zeroes the cell counters and bins particles [first, first + count) (all of them hold particles:
+ *           *buf->n_valid is not read here, it is written after this pass); d_idx_left / d_idx_right
  *           (each `cap` entries, may be NULL) receive the boundary-layer indices in arrival order, their
  *           numbers go to sph_status.halo_count (which may exceed cap: SPH_F_HALO_OVERFLOW at pack time)
  *   add     bins a further range (the ghost slots; slots >= *buf->n_valid go to the spare cell)

@@ -1403,7 +1403,8 @@ int sph_cells_begin(const sph_grid *g, const sph_buffers *b, const double *d_r, 
     cudaMemsetAsync(b->cell_count, 0, sizeof(uint32_t) * ((size_t)g->ncode + 1), s);
     const HaloLists hl = {d_idx_left, d_idx_right, (uint32_t)cap};
     if (count > 0)
-        bin_kernel<<<blocks_for(count, kBlock), kBlock, 0, s>>>(*g, d_r, first, count, b->n_valid, b->n_owned,
+        // no n_valid here: it is written by sph_halo_unpack AFTER this pass (the range binned first holds particles)
+        bin_kernel<<<blocks_for(count, kBlock), kBlock, 0, s>>>(*g, d_r, first, count, nullptr, b->n_owned,
                                                                 b->cell_count, b->code, b->rank, b->status, hl);
     return launch_status();
 }

@@ -72,6 +72,7 @@ def _worker(rank, world, port, q):
         ev._set_halo_cap(64)
         ev.evaluate()
         ev.check()
+        res["halo_cap"] = ev.halo_cap
         res["halo_regrown"] = ev.halo_cap > 64 and all(
             np.array_equal(res[kx], ev.result[kx].cpu().numpy()) for kx in ("rho", "p", "vdot", "udot"))
         out = [None] * world
@@ -142,7 +143,6 @@ def test_slab_evaluation_matches_oracle(world):
     assert np.array_equal(np.sort(gid), np.arange(n))
     # the overflow forced on the last rank grew every rank's capacity
     assert res[-1]["K0"] == 12 and all(x["K"] == res[0]["K"] and x["K"] > 12 for x in res)
-    assert all(x["same_bits"] and x["halo_regrown"] for x in res)
     assert all(min(x["ghosts"]) > 0 for x in res)
     for k in ("rho", "p", "vdot", "udot"):
         got = np.concatenate([x[k] for x in res])
@@ -150,6 +150,8 @@ def test_slab_evaluation_matches_oracle(world):
         full[gid] = got
         scale = np.maximum(np.abs(ref[k]), 1e-3 * np.max(np.abs(ref[k])))
         assert np.max(np.abs(full - ref[k]) / scale) < 1e-10, k
+    assert all(x["same_bits"] for x in res), [x["same_bits"] for x in res]
+    assert all(x["halo_regrown"] for x in res), [(x["halo_regrown"], x["halo_cap"]) for x in res]
 
 
 # ------------------------------------------------------------------ time stepping over the slabs
@@ -158,7 +160,8 @@ STEP_DT, STEP_N, STEP_T, STEP_TOL = 0.02, 3, 1.2, 1.0
 
 def _step_inputs(world):
     from oracle import oracle as O
-    r, v, box = O.lattice_workload(12 * world, 12, 12, seed=43, jitter=0.25, vmax=3.0)     # fast: some change rank
+    r, v, box = O.lattice_workload(12 * world, 12, 12, seed=43, jitter=0.3, vmax=8.0)     # fast: some change rank; relative
+    # displacement per stage 0.16 < list radius - h = 0.236, so the once-per-step list of the single-process run stays complete
     t = 1.0 + 0.2 * np.random.default_rng(3).random(r.shape[0])
     return r, v, box, t
 
@@ -216,9 +219,13 @@ def test_slab_stepper_on_cuda_matches_single_process_update(world):
     p.nlists.append(nl)
     p.nl_default = nl
     p.forces.append(forces.SpamForce(p, nl, cutoff=FCUT))
-    for _ in range(STEP_N):
-        nl.rebuild_list = True
-        p.update(STEP_DT)
+    sprops, particles.SPROPS = particles.SPROPS, True                  # spam_properties inside derivatives()
+    try:
+        for _ in range(STEP_N):
+            nl.rebuild_list = True
+            p.update(STEP_DT)
+    finally:
+        particles.SPROPS = sprops
     gid = np.concatenate([x["gid"] for x in res])
     assert np.array_equal(np.sort(gid), np.arange(n))
     assert sum(x["moved"] for x in res) > 0
