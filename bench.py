@@ -14,7 +14,11 @@ Workloads (number density 1, h = cutoff = 2.0, tolerance 0, force cutoff 5, EOS 
            (weak scaling: the box grows along x, slab-decomposed; 4 GPUs = the 64 Mi box of configs[3])
     c2     2-D sheet 1024x1024x1 in a 1024-deep box (configs[1])
     c4     3-D 512x512x256 = 64 Mi particles in total, strong-scaled over the GPUs (configs[3])
+    c5     neighbour-list build only (test/time_nlist.py's protocol: the list, not the forces), 2^26 particles per GPU
+           (configs[4])
     small  3-D 64^3 (quick functional run)
+--all-configs appends a `configs` block to the JSON line (outside the timed headline): c2 with its own roofline,
+c4 strong-scaled when N > 1, and the c5 build-only point.
 
 --impl reference times the reference's own CPU implementation (oracle/_ref, built from the
 unmodified reference sources by oracle/make_ref.py) on a bounded sample of the same workload.
@@ -43,6 +47,8 @@ WORKLOADS = {
                name="2D periodic SPH sheet 1024x1024 (1 Mi particles) per GPU in a 1024-deep box"),
     "c4": dict(dims=(512, 512, 256), zbox=None, scaling="strong",
                name="3D periodic SPH box 512x512x256 (64 Mi particles) in total"),
+    "c5": dict(dims=(512, 512, 256), zbox=None, scaling="weak", build_only=True,
+               name="neighbour-list build only (cell list + Morton reorder + neighbour pass), 2^26 particles per GPU"),
     "small": dict(dims=(64, 64, 64), zbox=None, scaling="weak", name="3D periodic SPH box 64^3 per GPU"),
 }
 H, CUTOFF, TOL, FCUT = 2.0, 2.0, 0.0, 5.0
@@ -292,6 +298,72 @@ def parity_gate(sim, wl, world, rank, device):
     return out
 
 
+def ncu_traffic(workload, world):
+    """dram__bytes_read + dram__bytes_write per launch of each pass from the committed `ncu --set full` capture
+    (profiles/r2_traffic.json, regenerated by profiles/summarise.py from the .ncu-rep of the same command); None
+    when there is no capture for this workload / GPU count."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as fh:
+            doc = json.load(fh)
+        return doc.get("%s_g%d" % (workload, world)), doc.get("source")
+    except Exception:
+        return None, None
+
+
+def side_run(name, world, rank, device, steps=5, warmup=3):
+    """One more BASELINE config, measured like the headline (CUDA events, max over ranks) but shorter: for the
+    `configs` block of --all-configs."""
+    import torch
+    import torch.distributed as dist
+    from pyticles_b200 import stepper
+    wl = WORKLOADS[name]
+    build_only = bool(wl.get("build_only"))
+    sim = stepper.make_bench_system(wl, world, rank, device, SEED, H, CUTOFF, TOL, FCUT, EOS)
+    for _ in range(warmup):
+        sim.evaluate(build_only=build_only)
+    sim.check()
+    sim.reset_pass_timers()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        sim.evaluate(timed=True, build_only=build_only)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tm = torch.tensor([ms], dtype=torch.float64, device=device)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+    st = sim.check()
+    passes, pairs = sim.pass_times(), sim.pairs_per_particle()
+    n_local, n_total = sim.n_owned, sim.n_total
+    peak, _ = peaks()
+    alg = {"cells+reorder": 24.0 + 2 * 72.0, "neighbour": 24.0 + 8.0 * pairs, "density": 80.0, "force": 112.0}
+    pass_out = {}
+    for k, t_ms in passes.items():
+        if build_only and k in ("density", "force"):
+            continue
+        pass_out[k] = {"ms": round(t_ms, 4)}
+        if k in alg and t_ms > 0:
+            gbs = alg[k] * n_local / (t_ms * 1e-3) / 1e9
+            pass_out[k].update(achieved_gbs=round(gbs, 1), frac=round(gbs / peak, 4))
+    dom = max((k for k in pass_out if k in alg), key=lambda k: pass_out[k]["ms"])
+    out = {"workload": wl["name"], "scaling": wl["scaling"], "particles_total": n_total, "steps": steps,
+           "ms_per_step": ms / steps, "value": n_total * steps / (ms * 1e-3),
+           "unit": "particles/s (list builds)" if build_only else UNIT,
+           "pairs_per_particle": round(pairs, 3), "pairs_per_s": round(pairs * n_total * steps / (ms * 1e-3), 1),
+           "tile_fallback": bool(st.flags & 32),
+           "roofline": {"pass": dom, "frac": pass_out[dom].get("frac"), "achieved": pass_out[dom].get("achieved_gbs"),
+                        "unit": "GB/s", "passes": pass_out}}
+    del sim
+    torch.cuda.empty_cache()
+    return out
+
+
 # ------------------------------------------------------------------ our arm
 _REAL_STDOUT = None
 
@@ -323,6 +395,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle parity gate (on by default)")
+    ap.add_argument("--all-configs", action="store_true",
+                    help="also measure c2, c4 (strong, N > 1) and the c5 build-only point; reported under `configs`")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -394,12 +468,25 @@ def main():
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             e2e["ms"] = float(tm.item())
 
+    configs = None
+    if args.all_configs:
+        configs = {}
+        names = ["c2"] + (["c4"] if (world > 1 and 512 % world == 0) else []) + ["c5"]
+        for nm in names:
+            if nm == args.workload:
+                continue
+            try:
+                configs[nm] = side_run(nm, world, rank, device)
+            except Exception as exc:                                # e.g. out of memory next to the headline system
+                configs[nm] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     peak, peak_src = peaks()
+    traffic, traffic_src = ncu_traffic(args.workload, world)
     value = n_total * args.steps / (ms * 1e-3)
     # algorithmic bytes per particle per launch (SURVEY.md section 8d / DESIGN.md)
     alg = {"cells+reorder": 24.0 + 2 * 72.0, "neighbour": 24.0 + 8.0 * pairs, "density": 80.0, "force": 112.0}
@@ -416,7 +503,7 @@ def main():
     roof = {"bound": "hbm", "kernel": sim.kernel_names[dom], "pass": dom,
             "achieved": pass_out[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
             "frac": pass_out[dom]["frac"],
-            "traffic": sim.ncu_traffic.get(dom) if (args.workload == "c3" and world == 1) else None,
+            "traffic": (traffic or {}).get(dom), "traffic_source": traffic_src if traffic else None,
             "algorithmic_bytes": round(alg[dom] * n_local, 1),
             "peak_source": peak_src,
             "whole_step": {"alg_bytes_per_particle": round(216.0 + 8.0 * pairs, 1),
@@ -444,6 +531,8 @@ def main():
                       "static_bytes": e2e["static"], "ms_per_step": e2e["ms"] / e2e["steps"],
                       "note": "r, v, t in and rho, p, vdot, udot out every step; m and h (constant between the "
                               "evaluations of a run) uploaded once = static_bytes"}
+    if configs:
+        out["configs"] = configs
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline()
     emit(out)

@@ -207,10 +207,14 @@ int sph_density_eos(const sph_grid *grid, const sph_buffers *buf, const sph_eos 
  * both NULL to reuse the values the preceding sph_density_eos left in vel4[.,3].
  * ACCUMULATES into vdot[n,3], udot[n] (original order) as the reference does; `first_force` != 0
  * says vdot / udot would be all zero at this point (particles.py:549-550 zeroes them before the first
- * force of an evaluation), so the results are stored instead and the caller need not zero them. */
+ * force of an evaluation), so the results are stored instead and the caller need not zero them.
+ * `part` splits the pass for the slab decomposition: 0 every particle, 1 all but the particles of the slab's two
+ * boundary cell layers (local x layers 1 and ncl[0] - 2 of a restricted grid), 2 only those -- the only ones with
+ * ghost neighbours, so part 1 can run while the ghosts' (p, rho) are still in flight. */
 int sph_force(const sph_grid *grid, const sph_buffers *buf, const double *d_press,
               const double *d_rho, const double *d_h_orig, int h_uniform, int list_fresh,
-              double fcutoff, int dim, int first_force, double *d_vdot, double *d_udot, void *stream);
+              double fcutoff, int dim, int first_force, int part, double *d_vdot, double *d_udot,
+              void *stream);
 
 /* Refresh press_i / rho_i^2 (the operand sph_force gathers) from original-order arrays for the
  * particles whose original index is >= first_orig only.  The slab decomposition uses it for the

@@ -116,7 +116,7 @@ SIGNATURES = {
     "sph_density_eos": (ctypes.c_int, [_gp, _bp, _ep, _vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        _vp, _vp, _vp, _vp, _vp, _vp]),
     "sph_force": (ctypes.c_int, [_gp, _bp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _dbl, ctypes.c_int,
-                                 ctypes.c_int, _vp, _vp, _vp]),
+                                 ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
     "sph_pressure_term": (ctypes.c_int, [_bp, _vp, _vp, _i32, _vp]),
     "sph_conduction": (ctypes.c_int, [_gp, _bp, _vp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),
     "sph_gradv": (ctypes.c_int, [_gp, _bp, _vp, _vp, ctypes.c_int, ctypes.c_int, _vp, _vp, _vp]),

@@ -168,9 +168,10 @@ class NeighbourBackend(object):
                                        _stream()), "sph_density_eos")
         self.press_ready = not long_range
 
-    def force(self, press, rho, h, h_uniform, fcutoff, dim, vdot, udot, reuse_press=False, first_force=False):
+    def force(self, press, rho, h, h_uniform, fcutoff, dim, vdot, udot, reuse_press=False, first_force=False, part=0):
         """`first_force`: vdot / udot would be all zero here (the evaluation's first force): results are stored,
-        the caller need not zero them (particles.py:549-550)."""
+        the caller need not zero them (particles.py:549-550).  `part`: 0 all particles, 1 all but the slab's
+        boundary layers, 2 only those (see sph_force)."""
         if reuse_press and self.press_ready:
             pp = rp = ctypes.c_void_p(0)
         else:
@@ -178,8 +179,8 @@ class NeighbourBackend(object):
             self.press_ready = False
         check(self.lib.sph_force(ctypes.byref(self.grid), ctypes.byref(self.buf), pp, rp, _ptr(_f64(h, "h")),
                                  int(bool(h_uniform)), int(self.fresh), float(fcutoff), int(dim),
-                                 int(bool(first_force)), _ptr(_f64(vdot, "vdot")), _ptr(_f64(udot, "udot")),
-                                 _stream()), "sph_force")
+                                 int(bool(first_force)), int(part), _ptr(_f64(vdot, "vdot")),
+                                 _ptr(_f64(udot, "udot")), _stream()), "sph_force")
 
     def pressure_term(self, press, rho, first_orig):
         """vel4[., 3] = press/rho^2 for the particles with original index >= first_orig (ghosts)."""

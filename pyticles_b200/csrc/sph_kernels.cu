@@ -256,7 +256,10 @@ gather_kernel(const __grid_constant__ sph_grid g, int n, const int32_t *__restri
     const CellLoc c = locate(g, x, y, z);
     store4(pos4 + 4 * (size_t)a, x, y, z, m[i]);
     store4(vel4 + 4 * (size_t)a, v[3 * i], v[3 * i + 1], v[3 * i + 2], 0.0);
-    reinterpret_cast<float4 *>(rel4)[a] = make_float4(c.rx, c.ry, c.rz, __uint_as_float(c.interior ? 1u : 0u));
+    // flags: bit 0 = interior cell (no minimum-image shift can occur), bit 1 = one of the two boundary cell layers
+    // of a slab (local x layers 1 and ncl[0] - 2 of a restricted grid: the particles whose neighbours include ghosts)
+    const uint32_t edge = (!g.wrap[0] && (c.cx == 1 || c.cx == g.ncl[0] - 2)) ? 2u : 0u;
+    reinterpret_cast<float4 *>(rel4)[a] = make_float4(c.rx, c.ry, c.rz, __uint_as_float((c.interior ? 1u : 0u) | edge));
 }
 
 // ------------------------------------------------------------------ neighbour pass
@@ -501,7 +504,7 @@ struct Interior {
 
 __device__ __forceinline__ bool cell_is_interior(const sph_grid &, uint32_t flag)
 {
-    return flag != 0u;       // computed once per particle by gather_kernel (rel4[., 3])
+    return (flag & 1u) != 0u;   // computed once per particle by gather_kernel (rel4[., 3]; bit 1: slab boundary layer)
 }
 
 constexpr int kRowU = SPH_ROW_U;             // neighbours gathered per pipeline stage
@@ -725,20 +728,24 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
              const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
              const int32_t *__restrict__ cnt, const sph_status *__restrict__ status,
              const double *__restrict__ h_orig, int list_fresh, double fcutsq, int dim, int n_owned, int store,
-             double *__restrict__ vdot, double *__restrict__ udot)
+             int part, double *__restrict__ vdot, double *__restrict__ udot)
 {
     const int gt = blockIdx.x * blockDim.x + threadIdx.x;
     const int a = gt / LPP, q = gt % LPP;
     const bool active = a < n;
     double px = 0, py = 0, pz = 0, pm = 0, vx = 0, vy = 0, vz = 0, Ai = 0;
     int count = 0, orig = 0;
-    bool interior = true;
+    bool interior = true, in_part = true;
     if (active) {
         load4(pos4 + 4 * (size_t)a, px, py, pz, pm);
         load4(vel4 + 4 * (size_t)a, vx, vy, vz, Ai);
         orig = perm[a];
         count = (n_owned > 0 && orig >= n_owned) ? 0 : min(cnt[a], K);       // nothing is computed for ghosts
-        interior = cell_is_interior(g, __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w));
+        const uint32_t fl = __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w);
+        interior = cell_is_interior(g, fl);
+        // part 1: every particle but those of the slab's boundary layers, part 2: only those (0: all)
+        in_part = part == 0 || ((fl & 2u) != 0u) == (part == 2);
+        if (!in_part) count = 0;
     }
     const bool can_skip = list_fresh && !(status->flags & (SPH_F_OUT_OF_BOX | SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
     const bool skip = __all_sync(0xffffffffu, interior) && can_skip;
@@ -756,7 +763,7 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
         f.az += __shfl_xor_sync(0xffffffffu, f.az, o);
         f.du += __shfl_xor_sync(0xffffffffu, f.du, o);
     }
-    if (!active || q != 0 || (n_owned > 0 && orig >= n_owned)) return;
+    if (!active || !in_part || q != 0 || (n_owned > 0 && orig >= n_owned)) return;
     (void)pm;
     // the reference accumulates into vdot/udot (particles.py:549-550 zeroes them per evaluation); `store` says this
     // is the first force after that zeroing, so the fill and the read-modify-write are both saved (0 + x == x)
@@ -1530,9 +1537,9 @@ int sph_density_eos(const sph_grid *g, const sph_buffers *b, const sph_eos *eos,
 
 int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, const double *d_rho,
               const double *d_h_orig, int h_uniform, int list_fresh, double fcutoff, int dim, int first_force,
-              double *d_vdot, double *d_udot, void *stream)
+              int part, double *d_vdot, double *d_udot, void *stream)
 {
-    if (!g || !b || !d_h_orig || !d_vdot || !d_udot) return SPH_E_BADARG;
+    if (!g || !b || !d_h_orig || !d_vdot || !d_udot || part < 0 || part > 2) return SPH_E_BADARG;
     if ((d_press == nullptr) != (d_rho == nullptr)) return SPH_E_BADARG;
     if (b->n == 0) return SPH_OK;
     cudaStream_t s = (cudaStream_t)stream;
@@ -1545,7 +1552,7 @@ int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, co
 #define SPH_LAUNCH_FORCE(U, L)                                                                                 \
     force_kernel<U, L><<<blocks_for((int64_t)b->n * L, kPPBlock), kPPBlock, 0, s>>>(                           \
         *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig,        \
-        list_fresh, fcutsq, dim, b->n_owned, first_force ? 1 : 0, d_vdot, d_udot)
+        list_fresh, fcutsq, dim, b->n_owned, first_force ? 1 : 0, part, d_vdot, d_udot)
     if (h_uniform) {
         if (lpp == 1) SPH_LAUNCH_FORCE(true, 1);
         else if (lpp == 2) SPH_LAUNCH_FORCE(true, 2);

@@ -129,7 +129,7 @@ gradv_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
         load4(aux4 + 4 * (size_t)a, vx, vy, vz, vw);
         count = min(cnt[a], K);
         orig = perm[a];
-        interior = __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w) != 0u;
+        interior = (__float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w) & 1u) != 0u;
     }
     const bool can_skip = list_fresh && !(status->flags & (SPH_F_OUT_OF_BOX | SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
     const bool skip = __all_sync(0xffffffffu, interior) && can_skip;
@@ -228,7 +228,7 @@ viscous_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *_
         load4(aux8 + 8 * (size_t)a + 4, S[4], S[5], s6, s7);
         count = min(cnt[a], K);
         orig = perm[a];
-        interior = __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w) != 0u;
+        interior = (__float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w) & 1u) != 0u;
     }
     const bool can_skip = list_fresh && !(status->flags & (SPH_F_OUT_OF_BOX | SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
     const bool skip = __all_sync(0xffffffffu, interior) && can_skip;
@@ -306,7 +306,7 @@ gradient_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *
         load4(aux4 + 4 * (size_t)a, fs, ws, e2, e3);
         count = min(cnt[a], K);
         orig = perm[a];
-        interior = __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w) != 0u;
+        interior = (__float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w) & 1u) != 0u;
     }
     const bool can_skip = list_fresh && !(status->flags & (SPH_F_OUT_OF_BOX | SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
     const bool skip = __all_sync(0xffffffffu, interior) && can_skip;
@@ -396,7 +396,7 @@ core_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__re
         load4(vel4 + 4 * (size_t)a, vx, vy, vz, vw);
         count = min(cnt[a], K);
         orig = perm[a];
-        interior = __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w) != 0u;
+        interior = (__float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w) & 1u) != 0u;
     }
     const bool can_skip = list_fresh && !(status->flags & (SPH_F_OUT_OF_BOX | SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
     const bool skip = __all_sync(0xffffffffu, interior) && can_skip;

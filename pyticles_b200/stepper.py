@@ -20,9 +20,6 @@ LAUNCHES_PER_EVAL = 13
 class SphEvaluator(object):
     kernel_names = {"cells+reorder": "bin_kernel+scan+scatter_kernel+cell_sort_kernel+gather_kernel",
                     "neighbour": "tile_list_kernel", "density": "density_kernel<true>", "force": "force_kernel<true>"}
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` on the c3 workload
-    # (profiles/r1f_kernels.txt); only meaningful for that workload
-    ncu_traffic = {"cells+reorder": None, "neighbour": 2.65e9, "density": 5.04e9, "force": 4.92e9}
 
     def __init__(self, p, nl, force, eos=(2.0, 0.5, 1.0)):
         self.p, self.nl, self.force, self.eos = p, nl, force, eos
@@ -45,9 +42,10 @@ class SphEvaluator(object):
         self.h_uniform = properties._h_uniform(p, p.h)
         self._planned = True
 
-    def evaluate(self, timed=False, io=None):
+    def evaluate(self, timed=False, io=None, build_only=False):
         """One derivative evaluation.  `io` (dict of tensors r v m h t rho p pco u vdot udot) selects
-        other input/output buffers than the particle system's own (used by the streamed e2e path)."""
+        other input/output buffers than the particle system's own (used by the streamed e2e path).
+        `build_only`: stop after the neighbour pass (BASELINE configs[4], the list-build sweep)."""
         if not self._planned:
             self._plan()
         p, be = self.p, self.nl.backend
@@ -63,6 +61,12 @@ class SphEvaluator(object):
         be.nlist()
         if timed:
             ev[2].record()
+        if build_only:
+            if timed:
+                for k in (3, 4):
+                    ev[k].record()
+                self._events.append(ev)
+            return
         be.density_eos(self.eos, x["h"], self.h_uniform, x["rho"], x["p"], x["pco"], x["u"], x["t"])
         if timed:
             ev[3].record()

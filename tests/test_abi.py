@@ -147,7 +147,8 @@ def test_variant_sweep_flags_exist_in_the_source():
     vs = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(vs)
     src = open(os.path.join(ROOT, "pyticles_b200", "csrc", "sph_kernels.cu")).read() + \
-        open(os.path.join(ROOT, "pyticles_b200", "csrc", "sph_tiles.cu")).read()
+        open(os.path.join(ROOT, "pyticles_b200", "csrc", "sph_tiles.cu")).read() + \
+        open(os.path.join(ROOT, "pyticles_b200", "csrc", "sph_tiles_mma.cu")).read()
     assert vs.VARIANTS["default"] == []
     for name, flags in vs.VARIANTS.items():
         for f in flags:

@@ -47,8 +47,8 @@ VARIANTS = {
     "w_f_ahead3": _v(W, SPH_IDX_AHEAD_F=3),
     "w_f_ahead4": _v(W, SPH_IDX_AHEAD_F=4),
     "w_f_r64": _v(W, SPH_FORCE_MINB=8),
-    # round 2: the cell-group neighbour kernel (csrc/sph_tiles.cu)
-    "t_b4": ["-DSPH_TILE_BLOCKS=4"],      # 4 blocks per SM: 64 registers, no spills
+    # round 2: the tensor-core variant of the neighbour kernel (csrc/sph_tiles_mma.cu; run with SPH_TILES=2)
+    "mma_b5": ["-DSPH_TILE_BLOCKS=5"],    # 5 blocks per SM (48 registers, spills), window capacity 1024
 }
 # The other rows of the r1f sweep tables (noalloc, keep, *_smq, *_maxl1, w_f_pipe_r80, w_stride8, w_pairload, w_intra)
 # were variants whose code was removed after they lost; they can be rebuilt from commit dac84c7.
