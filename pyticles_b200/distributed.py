@@ -191,11 +191,12 @@ class SlabSphEvaluator(object):
         vol = box[0] * box[1] * box[2]
         rl = (cutoff * cutoff + tol * tol) ** 0.5
         self.be.user_max_nbrs = int(1.35 * 4.18879 * rl ** 3 * self.n_total / vol) + 16
-        # 13 of one GPU + second binning pass (ghosts) + halo pack / unpack (x2) + pressure_term + second force part
-        self.launches_per_eval = 13 if self.dec.world == 1 else 20
+        # 13 of one GPU + second binning pass (ghosts) + halo pack / unpack (x2) + pressure_term
+        self.launches_per_eval = 13 if self.dec.world == 1 else 19
         self._events = []
         self._nvalid = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._halo_buf = None
+        self.overlap_b = False
         if self.dec.world > 1:
             if halo_cap is None:
                 # a boundary layer holds n_owned / owned layers particles on average
@@ -354,22 +355,17 @@ class SlabSphEvaluator(object):
         be.density_eos(self.eos, self.h_global, True, rho, p, pco, u, t)
         if timed:
             ev[5].record()
-        if multi:
-            # B: (p, rho) of the ghosts travel on a side stream while the force pass runs over every particle that
-            # has no ghost neighbour (all but the two boundary cell layers); the boundary layers follow
+        if multi and self.overlap_b:
+            # B on a side stream while the force pass runs over every particle that has no ghost neighbour (all but
+            # the two boundary cell layers); the boundary layers follow.  Measured on 2 B200s it LOSES: the two force
+            # launches cost 0.5 ms more than the one, exchange B only 0.2 ms (profiles/r2_halo.txt) -- off by default.
             main = torch.cuda.current_stream()
             side = self._side_stream()
             done_density = torch.cuda.Event()
             done_density.record(main)
             with torch.cuda.stream(side):
                 side.wait_event(done_density)
-                st2 = ctypes.c_void_p(side.cuda_stream)
-                _lib.check(L.sph_halo_pack2(_P(idx[0]), _P(idx[1]), cap, _P(p), _P(rho), _P(sb[0]), _P(sb[1]), stat, st2),
-                           "sph_halo_pack2")
-                dec.ring_exchange(sb[0], sb[1], rb[0], rb[1])
-                _lib.check(L.sph_halo_unpack2(_P(rb[0]), _P(rb[1]), cap, no, _P(p), _P(rho), stat, st2),
-                           "sph_halo_unpack2")
-                be.pressure_term(p, rho, no)                  # only the ghosts need their p/rho^2 refreshed
+                self._exchange_b(L, idx, sb, rb, cap, no, p, rho, stat, ctypes.c_void_p(side.cuda_stream))
                 done_b = torch.cuda.Event()
                 done_b.record(side)
             be.force(p, rho, self.h_global, True, self.fcut, 3, vdot, udot, reuse_press=True, first_force=True, part=1)
@@ -378,6 +374,8 @@ class SlabSphEvaluator(object):
             main.wait_event(done_b)
             be.force(p, rho, self.h_global, True, self.fcut, 3, vdot, udot, reuse_press=True, first_force=True, part=2)
         else:
+            if multi:                                                                          # B
+                self._exchange_b(L, idx, sb, rb, cap, no, p, rho, stat, st)
             if timed:
                 ev[6].record()
             be.force(p, rho, self.h_global, True, self.fcut, 3, vdot, udot, reuse_press=True, first_force=True)
@@ -385,6 +383,14 @@ class SlabSphEvaluator(object):
             ev[7].record()
             self._events.append(ev)
         self.result = dict(rho=rho[:no], p=p[:no], pco=pco[:no], u=u[:no], vdot=vdot[:no], udot=udot[:no])
+
+    def _exchange_b(self, L, idx, sb, rb, cap, no, p, rho, stat, st):
+        """(p, rho) of the boundary-layer particles to the neighbours' ghost slots, same particles and order as A."""
+        _lib.check(L.sph_halo_pack2(_P(idx[0]), _P(idx[1]), cap, _P(p), _P(rho), _P(sb[0]), _P(sb[1]), stat, st),
+                   "sph_halo_pack2")
+        self.dec.ring_exchange(sb[0], sb[1], rb[0], rb[1])
+        _lib.check(L.sph_halo_unpack2(_P(rb[0]), _P(rb[1]), cap, no, _P(p), _P(rho), stat, st), "sph_halo_unpack2")
+        self.be.pressure_term(p, rho, no)                     # only the ghosts need their p/rho^2 refreshed
 
     def _side_stream(self):
         if getattr(self, "_side", None) is None:
@@ -424,17 +430,19 @@ class SlabSphEvaluator(object):
         self._events = []
 
     def pass_times(self):
-        """Mean ms per pass.  `halo` is exchange A (pack, ring send/recv, unpack); exchange B runs on a side stream
-        under the interior part of the force pass, so what of it is exposed shows up in `force` (interior part +
-        wait + boundary-layer part)."""
-        names = ["cells_own", "halo", "cells+reorder", "neighbour", "density", "force_interior", "force_boundary"]
+        """Mean ms per pass.  `halo` is exchange A + exchange B (pack, ring send/recv, unpack); with `overlap_b`
+        exchange B hides under the interior part of the force pass and shows up in `force` instead."""
+        names = ["cells_own", "halo", "cells+reorder", "neighbour", "density", "halo_b", "force"]
         tot = dict.fromkeys(names, 0.0)
         for ev in self._events:
             for k, nm in enumerate(names):
                 tot[nm] += ev[k].elapsed_time(ev[k + 1])
         k = max(1, len(self._events))
         out = {nm: tot[nm] / k for nm in names}
-        out["force"] = out.pop("force_interior") + out.pop("force_boundary")
+        if self.overlap_b:
+            out["force"] += out.pop("halo_b")                 # interior part; the boundary part is in "force"
+        else:
+            out["halo"] += out.pop("halo_b")
         out["cells+reorder"] += out.pop("cells_own")
         return out
 

@@ -68,6 +68,12 @@ def _worker(rank, world, port, q):
         ev.evaluate()
         ev.check()
         res["same_bits"] = all(np.array_equal(res[kx], ev.result[kx].cpu().numpy()) for kx in ("rho", "p", "vdot", "udot"))
+        # exchange B under the interior force pass (force split by boundary layers): the same bits
+        ev.overlap_b = True
+        ev.evaluate()
+        ev.check()
+        res["overlap_same"] = all(np.array_equal(res[kx], ev.result[kx].cpu().numpy()) for kx in ("rho", "p", "vdot", "udot"))
+        ev.overlap_b = False
         # a halo buffer that is too small is grown collectively as well
         ev._set_halo_cap(64)
         ev.evaluate()
@@ -150,7 +156,7 @@ def test_slab_evaluation_matches_oracle(world):
         full[gid] = got
         scale = np.maximum(np.abs(ref[k]), 1e-3 * np.max(np.abs(ref[k])))
         assert np.max(np.abs(full - ref[k]) / scale) < 1e-10, k
-    assert all(x["same_bits"] for x in res), [x["same_bits"] for x in res]
+    assert all(x["same_bits"] and x["overlap_same"] for x in res), [(x["same_bits"], x["overlap_same"]) for x in res]
     assert all(x["halo_regrown"] for x in res), [(x["halo_regrown"], x["halo_cap"]) for x in res]
 
 
