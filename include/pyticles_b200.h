@@ -272,12 +272,13 @@ int sph_core_force(const sph_grid *grid, const sph_buffers *buf, double sigma, d
 /* ------------------------------------------------------------------ pair-list API surface */
 
 /* Lexicographic i<j pair list in ORIGINAL indices (what VerletList.build leaves in
- * nl.iap, neighbour_list.py:186-189).  Two calls: count fills d_row_start[n+1] (exclusive
- * scan of pairs per original i; d_row_start[n] = nip), fill writes iap[nip,2] (int32). */
+ * nl.iap, neighbour_list.py:186-189).  Two calls: count fills d_row_count[n] (pairs per original i); the caller
+ * scans it into d_row_start[n+1] as 64-BIT offsets (d_row_start[n] = nip: a 256 Mi-particle box holds 4.5e9 pairs,
+ * more than 32 bits count); fill writes iap[nip,2] (int32 particle indices). */
 int sph_pairs_count(const sph_buffers *buf, uint32_t *d_row_count, void *stream);
-int sph_pairs_fill(const sph_buffers *buf, const uint32_t *d_row_start, int32_t *d_iap,
+int sph_pairs_fill(const sph_buffers *buf, const int64_t *d_row_start, int32_t *d_iap,
                    int64_t cap_pairs, void *stream);
-/* Exclusive scan helper used between the two (also used by sph_cells_build). */
+/* Exclusive 32-bit scan (used by sph_cells_build; exported for callers with short lists). */
 int sph_exclusive_scan_u32(const uint32_t *d_in, uint32_t *d_out, uint32_t *d_tmp, int64_t n,
                            void *stream);
 

@@ -252,11 +252,11 @@ class NeighbourBackend(object):
         if n == 0:
             return torch.zeros((0, 2), dtype=torch.int32, device=self.device)
         row_count = torch.empty(n, dtype=torch.int32, device=self.device)
-        row_start = torch.empty(n + 1, dtype=torch.int32, device=self.device)
-        tmp = torch.empty(int(L.sph_scan_tmp_elems(n)), dtype=torch.int32, device=self.device)
         check(L.sph_pairs_count(b, _ptr(row_count), s), "sph_pairs_count")
-        check(L.sph_exclusive_scan_u32(_ptr(row_count), _ptr(row_start), _ptr(tmp), n, s), "sph_exclusive_scan_u32")
-        nip = int(row_start[n].item()) & 0xFFFFFFFF
+        # 64-bit offsets: more than 2^32 pairs must not wrap (the scan is a torch op: this is the export, not the hot path)
+        row_start = torch.zeros(n + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(row_count.to(torch.int64), dim=0, out=row_start[1:])
+        nip = int(row_start[n].item())
         iap = torch.empty((nip, 2), dtype=torch.int32, device=self.device)
         check(L.sph_pairs_fill(b, _ptr(row_start), _ptr(iap), nip, s), "sph_pairs_fill")
         return iap

@@ -915,7 +915,7 @@ constexpr int kExportMax = 256;   // neighbours sorted in local memory per parti
 
 __global__ void __launch_bounds__(128)
 pairs_fill_kernel(int n, int K, const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
-                  const int32_t *__restrict__ cnt, const uint32_t *__restrict__ row_start,
+                  const int32_t *__restrict__ cnt, const int64_t *__restrict__ row_start,
                   int32_t *__restrict__ iap, int64_t cap)
 {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1495,11 +1495,8 @@ int sph_nlist_build(const sph_grid *g, const sph_buffers *b, void *stream)
     // the cell-group kernel first; the general kernel behind it returns at once unless that one gave up.
     // SPH_TILES in the environment: 0 general kernel only, 1 (default) scalar cell-group kernel, 2 its tensor-core
     // pre-filter variant (tests, A/B timing)
-    static int mode = -1;
-    if (mode < 0) {
-        const char *e = getenv("SPH_TILES");
-        mode = e ? atoi(e) : 1;
-    }
+    const char *env = getenv("SPH_TILES");                 // read at every call: tests switch it
+    const int mode = env ? atoi(env) : 1;
     const bool mma = mode == 2 && sph_tiles_mma::eligible(g, b);
     const bool tiles = mma || (mode != 0 && sph_tiles::eligible(g, b));
     if (tiles) {
@@ -1602,7 +1599,7 @@ int sph_pairs_count(const sph_buffers *b, uint32_t *d_row_count, void *stream)
     return launch_status();
 }
 
-int sph_pairs_fill(const sph_buffers *b, const uint32_t *d_row_start, int32_t *d_iap, int64_t cap_pairs, void *stream)
+int sph_pairs_fill(const sph_buffers *b, const int64_t *d_row_start, int32_t *d_iap, int64_t cap_pairs, void *stream)
 {
     if (!b || !d_row_start || (!d_iap && cap_pairs > 0)) return SPH_E_BADARG;
     if (b->n > 0 && cap_pairs > 0)

@@ -2,28 +2,31 @@
 //
 // One block works on a GROUP of 2 x 2 x 2 cells (eight consecutive block-Morton codes), one warp
 // per cell.  The block stages the 4 x 4 x 4 cells around the group ONCE in shared memory as fp32
-// positions in the group's frame, so a particle row is read from L2 8x instead of 27x, with
-// coalesced loads.
+// positions in the group's frame (origin at the corner the eight cells share) with their squared norm, so a
+// particle row is read from L2 8x instead of 27x, with coalesced loads.
 //
 // A warp takes the particles of its cell up to 16 at a time.  Inside a pass, lane = q * P + p:
-// particle p (of P) and candidate stream q of Q = 32 / P.  A lane walks every Q-th candidate of the
-// 9 window columns (3 cells each, contiguous in the staged window) around its cell and keeps its
-// own list of hits -- no ballot, no popc, one predicated shared store per hit; 14 instructions per
-// 32 tests against 26 in the warp-per-cell kernel of sph_kernels.cu.  The Q lists of a particle are
-// then concatenated, in a fixed order, into its warp-transposed ELL row (the neighbour structure
+// particle p (of P) and candidate stream q of Q = 32 / P.  A lane walks every Q-th candidate of the 9 window columns (3 cells each, contiguous in the
+// staged window) around its cell and keeps its own list of hits -- no ballot, no popc, one predicated shared
+// store per hit.  One test is the dot-product form
+//     d = |c|^2 + (|p|^2 - thr_out) - 2 c.p        1 FADD + 3 FFMA  (|c|^2 staged with the position, -2p per lane)
+// with a running minimum of |d| for the error band: 8 instructions with the LDS.128 and the hit bookkeeping
+// (r1: 12 with three subtractions, a multiply, two FFMA and a maximum of the accepted rsq).  The Q lists of a
+// particle are then concatenated, in a fixed order, into its warp-transposed ELL row (the neighbour structure
 // every other pass and the export use).
 //
-// Exactness is the one of the general kernel: rsq32 < thr_in accepts, rsq32 >= thr_out rejects,
-// hits inside the fp32 error band are decided by the reference's fp64 predicate (pair_exact).
-// Cases outside the fixed capacities (> 64 particles in a cell, > 32 hits in one stream's list even
-// at Q >= 4, > 1280 particles in the 64 cells of a window, positions far outside the box) raise
+// Exactness is the one of the general kernel: d < -bw accepts, d >= 0 rejects (rsq32 >= thr_out), a lane that saw
+// |d| < bw (the rigorous fp32 error band, tile_thresholds) re-decides all its hits with the reference's fp64
+// predicate (pair_exact).  Cases outside the fixed capacities (> 64 particles in a cell, > 32 hits in one stream's
+// list even at Q >= 4, > 1024 particles in the 64 cells of a window, positions far outside the box) raise
 // SPH_F_TILE_FALLBACK and the general kernel redoes the pass.
 //
 // Round 2 tried three other formulations of this pass, each exact and tested, none faster on B200 (DESIGN.md section 5,
-// profiles/r2_tile_*): bit-mask bookkeeping instead of per-lane lists (fewer test instructions, but walking the masks
-// keeps a third of the lanes busy: 5.4 ms against 4.4), the dot-product form of the test with strides compiled per Q
-// (11 % fewer instructions, but four copies of the unrolled column code miss the instruction cache: 4.9 ms; with one
-// copy 4.6 ms), and a tensor-core pre-filter (sph_tiles_mma.cu, SPH_TILES=2: 5.7 ms).
+// profiles/r2_tile_experiments.txt): bit-mask bookkeeping instead of per-lane lists (fewer test instructions, but
+// walking the masks keeps a third of the lanes busy: 5.4 ms), the pass body compiled per Q so that every stride is an
+// immediate (11 % fewer instructions, but four copies of the unrolled column code miss the instruction cache: 4.9 ms),
+// and a tensor-core pre-filter (sph_tiles_mma.cu, SPH_TILES=2: 5.7 ms).  What stayed is the dot-product form of the
+// test with one copy of the pass: 4.26 ms against r1's 4.37.
 //
 // Reference semantics (file:line into the reference tree):
 //   pair predicate     neighbour_list.py:105-123,170-178
@@ -36,15 +39,17 @@ namespace {
 
 constexpr int kTWarps = 8;           // warps per block = cells per group
 constexpr int kTThreads = kTWarps * 32;
-constexpr int kTCap = 1280;          // staged candidates per group (64 cells); 1536 still fits 5 blocks per SM but
-                                     // leaves 13 KB of L1: 4.46 against 4.35 ms on 256^3
+constexpr int kTCap = 1024;          // staged candidates per group (64 cells).  1280 would be 44 KB per block: the
+                                     // fifth block no longer fits an SM and the pass takes 4.61 instead of 4.26 ms
 constexpr int kTPass = 16;           // particles of a cell per pass (Q = 32 / P >= 2 streams each); 8 when lists overflow
 constexpr int kTPart = 64;           // particles per cell the tile path handles (cell width ~2 lattice planes: 8 .. 27)
-constexpr int kTQMax = 8;            // candidate streams per particle at most
 constexpr int kTRow = 32;            // hits one lane (one stream of one particle) can hold
 typedef uint16_t entry_t;            // a hit is the 16-bit shared address of the staged candidate
 constexpr int kTRowS = 34;           // list stride in shared memory (entries; 17 words: lanes fall in distinct banks)
-constexpr int kTBlocks = 5;          // resident blocks per SM (38 KB of shared memory, 48 registers)
+#ifndef SPH_TILE_BLOCKS
+#define SPH_TILE_BLOCKS 5
+#endif
+constexpr int kTBlocks = SPH_TILE_BLOCKS;   // resident blocks per SM (39 KB of shared memory; 5: 48 registers)
 
 constexpr uint32_t kFull = 0xffffffffu;
 
@@ -56,25 +61,26 @@ struct TileArgs {
     int32_t *nbr;
     int32_t *cnt;
     sph_status *status;
-    float thr_in, thr_out;
+    float thr_out, bw;       // d = rsq32 - thr_out; hits with d >= -bw are settled in fp64
     int pass0;               // particles of a cell per pass to start with (16 or 8)
     const int32_t *perm;
     int n_owned;             // > 0: cells of ghosts (original index >= n_owned) get empty rows
 };
 
-// shared memory of a block: [S32 | B | Head]
+// shared memory of a block: [S32 | I32 | B | Head]
 struct Head {
     uint32_t off[68];        // exclusive scan of cnt (65 used)
     uint32_t start[64];      // first sorted particle of window cell (wz*4 + wy)*4 + wx
     uint32_t cnt[64];
-    float shift[12];         // (i - 1) * w[d] at [4 d + i]: fp32 frame shift of window layer i
+    float shift[12];         // (i - 2) * w[d] at [4 d + i]: fp32 frame shift of window layer i
     uint32_t part[12];       // cell code contribution of window layer i of dimension d at [4 d + i]; ~0u: no such layer
     int gc[4];               // local cell coordinates of the group's base cell
 };
 
 constexpr size_t kBytesS32 = sizeof(float4) * kTCap;
+constexpr size_t kBytesI32 = sizeof(uint32_t) * kTCap;
 constexpr size_t kBytesB = sizeof(entry_t) * kTWarps * 32 * kTRowS;
-constexpr size_t kSmemList = kBytesS32 + kBytesB + sizeof(Head);
+constexpr size_t kSmemList = kBytesS32 + kBytesI32 + kBytesB + sizeof(Head);
 static_assert(kTBlocks * (kSmemList + 1024) <= 227 * 1024, "blocks per SM");
 static_assert(kBytesS32 + 1024 < 65536, "hits are kept as 16-bit shared addresses of the staged candidate");
 
@@ -85,10 +91,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p)
 
 // ------------------------------------------------------------------ window of a group
 // Fills Head (window cells, their scan, frame shifts, base coordinates) and stages the window:
-// S32 = fp32 position in the group's frame + sorted index.  Returns the number of staged
-// candidates (> kTCap: nothing was staged).
+// S32 = fp32 position in the group's frame + its squared norm, I32 = sorted index.  Returns the number of
+// staged candidates (> kTCap: nothing was staged).
 __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, const TileArgs &a, Head *H,
-                                               float4 *S32)
+                                               float4 *S32, uint32_t *I32)
 {
     const int t = threadIdx.x;
     if (t < 12) {
@@ -99,7 +105,7 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
         int cc[3];
         cell_coords(g, c0, cc[0], cc[1], cc[2]);
         if (t == 0) { H->gc[0] = cc[0]; H->gc[1] = cc[1]; H->gc[2] = cc[2]; }
-        H->shift[t] = (float)((double)(i - 1) * g.w[d]);
+        H->shift[t] = (float)((double)(i - 2) * g.w[d]);
         int c = cc[d] + i - 1;
         bool ok = true;
         if (c < 0) {
@@ -154,7 +160,9 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
         const float fx = H->shift[wc & 3], fy = H->shift[4 + ((wc >> 2) & 3)], fz = H->shift[8 + (wc >> 4)];
         for (uint32_t k = lane & 7; k < cn; k += 8) {
             const float4 p = __ldg(rel + st + k);
-            S32[dst + k] = make_float4(p.x + fx, p.y + fy, p.z + fz, __int_as_float((int)(st + k)));
+            const float x = p.x + fx, y = p.y + fy, z = p.z + fz;
+            S32[dst + k] = make_float4(x, y, z, fmaf(z, z, fmaf(y, y, x * x)));
+            I32[dst + k] = st + k;
         }
     }
     __syncthreads();
@@ -182,69 +190,118 @@ __device__ __forceinline__ HomeCell home_cell(const sph_grid &g, const Head *H, 
     return h;
 }
 
-// lane = q * P + p: particle p (of the P <= 16 of this pass), candidate stream q (of Q = 32 / P)
-struct LaneMap {
-    int Q, lgq, p, q;
-    bool active;             // q < Q
-};
+#define SPH_LDS4(X, Y, Z, W, ADDR) \
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(X), "=f"(Y), "=f"(Z), "=f"(W) : "r"(ADDR))
 
-__device__ __forceinline__ LaneMap lane_map(int P, int lane)
-{
-    LaneMap m;
-    m.Q = P <= 4 ? kTQMax : 32 / P;
-    m.lgq = 31 - __clz(m.Q);
-    m.q = (int)(((float)lane + 0.5f) * __frcp_rn((float)P));     // lane / P: never within 1/64 of an integer
-    m.p = lane - m.q * P;
-    m.active = m.q < m.Q;
-    return m;
-}
-
-// One candidate stream of one window column against one home particle, two candidates per trip.
-// A hit (rsq32 < thr_out) is kept as the 16-bit shared address of the staged candidate; the band
-// [thr_in, thr_out) is settled by the caller from `maxacc`.  SELF: the column holds the particle itself.
+// One candidate against one home particle: d = rsq32 - thr_out in the dot-product form.  A hit (d < 0) is kept as
+// the 16-bit shared address of the staged candidate; the band [-bw, 0) is settled by the caller from `near`.
+// SELF: the column holds the particle itself.
 template <bool CHECK, bool SELF>
-__device__ __forceinline__ void test_one(uint32_t ptr, uint32_t selfptr, const float4 &hp, float thr_out,
-                                         float cx, float cy, float cz, uint32_t &lp, uint32_t lp_lim,
-                                         float &maxacc, bool &over)
+__device__ __forceinline__ void test_one(uint32_t ptr, uint32_t selfptr, float px2, float py2, float pz2, float Kp,
+                                         float cx, float cy, float cz, float cn, uint32_t &lp, uint32_t lp_lim,
+                                         float &near, bool &over)
 {
-    const float dx = cx - hp.x, dy = cy - hp.y, dz = cz - hp.z;
-    const float rsq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    if (rsq < thr_out && (!SELF || ptr != selfptr)) {
+    const float d = fmaf(cz, pz2, fmaf(cy, py2, fmaf(cx, px2, cn + Kp)));
+    near = fminf(near, fabsf(d));
+    if (d < 0.f && (!SELF || ptr != selfptr)) {
         if (CHECK && lp >= lp_lim) {
             over = true;
         } else {
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(lp), "h"((unsigned short)ptr) : "memory");
             lp += (uint32_t)sizeof(entry_t);
-            maxacc = fmaxf(maxacc, rsq);
         }
     }
 }
 
-#define SPH_LDS4(X, Y, Z, W, ADDR) \
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(X), "=f"(Y), "=f"(Z), "=f"(W) : "r"(ADDR))
-
+// One candidate stream (every Q-th candidate from ptr on, below pend; step = 16 Q) of one window column, two per trip
 template <bool CHECK, bool SELF>
-__device__ __forceinline__ void test_column(uint32_t ptr, uint32_t pend, uint32_t step, uint32_t selfptr,
-                                            const float4 &hp, float thr_out, uint32_t &lp, uint32_t lp_lim,
-                                            float &maxacc, bool &over)
+__device__ __forceinline__ void test_column(uint32_t ptr, uint32_t pend, uint32_t step, uint32_t selfptr, float px2,
+                                            float py2, float pz2, float Kp, uint32_t &lp, uint32_t lp_lim, float &near,
+                                            bool &over)
 {
-    float ax, ay, az, aw, bx, by, bz, bw;
+    float ax, ay, az, an, bx, by, bz, bn;
     for (; ptr + step < pend; ptr += 2u * step) {                        // two loads in flight
-        SPH_LDS4(ax, ay, az, aw, ptr);
-        SPH_LDS4(bx, by, bz, bw, ptr + step);
-        test_one<CHECK, SELF>(ptr, selfptr, hp, thr_out, ax, ay, az, lp, lp_lim, maxacc, over);
-        test_one<CHECK, SELF>(ptr + step, selfptr, hp, thr_out, bx, by, bz, lp, lp_lim, maxacc, over);
+        SPH_LDS4(ax, ay, az, an, ptr);
+        SPH_LDS4(bx, by, bz, bn, ptr + step);
+        test_one<CHECK, SELF>(ptr, selfptr, px2, py2, pz2, Kp, ax, ay, az, an, lp, lp_lim, near, over);
+        test_one<CHECK, SELF>(ptr + step, selfptr, px2, py2, pz2, Kp, bx, by, bz, bn, lp, lp_lim, near, over);
     }
     if (ptr < pend) {
-        SPH_LDS4(ax, ay, az, aw, ptr);
-        test_one<CHECK, SELF>(ptr, selfptr, hp, thr_out, ax, ay, az, lp, lp_lim, maxacc, over);
+        SPH_LDS4(ax, ay, az, an, ptr);
+        test_one<CHECK, SELF>(ptr, selfptr, px2, py2, pz2, Kp, ax, ay, az, an, lp, lp_lim, near, over);
     }
+}
+
+// One pass: P <= 32 / Q particles of the home cell (first at window index c0, sorted index cs), lane = q * P + p
+// (particle p, candidate stream q of Q).  Returns the longest row written, or ~0u when a stream's list overflowed.
+// (Compiling the pass per Q makes every stride an immediate and saves 11 % of the instructions, but the four
+// copies of the unrolled column code no longer fit the instruction cache: 4.89 against 4.37 ms, profiles/r2_tile_*.)
+__device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs &a, const float4 *S32,
+                                              const uint32_t *I32, entry_t *B, const uint32_t *offh, uint32_t c0,
+                                              uint32_t cs, int P, int Q, int lane)
+{
+    const uint32_t step = (uint32_t)Q * 16u, qmagic = (65536u + (uint32_t)Q - 1u) / (uint32_t)Q;
+    const int q = (int)(((float)lane + 0.5f) * __frcp_rn((float)P));     // lane / P: never within 1/64 of an integer
+    const int p = lane - q * P;
+    const bool active = q < Q;
+    const uint32_t selfc = c0 + (uint32_t)p, asorted = cs + (uint32_t)p;
+    const uint32_t s32a = smem_u32(S32), s16 = s32a & 0xffffu, selfptr = s32a + selfc * 16u;
+    const float4 hp = S32[selfc];
+    const float px2 = -2.0f * hp.x, py2 = -2.0f * hp.y, pz2 = -2.0f * hp.z, Kp = hp.w - a.thr_out;
+    const uint32_t lp0 = smem_u32(B), lp_lim = lp0 + (uint32_t)sizeof(entry_t) * kTRow;
+    uint32_t lp = lp0;
+    float near = INFINITY;
+    bool over = false;
+    if (active) {
+#pragma unroll
+        for (int col = 0; col < 9; ++col) {                              // unrolled: 4.43 ms against 4.55 ms as a loop
+            const uint32_t s = offh[((col / 3) * 4 + col % 3) * 4], e = offh[((col / 3) * 4 + col % 3) * 4 + 3];
+            const uint32_t pend = s32a + e * 16u, pbeg = s32a + (s + (uint32_t)q) * 16u;
+            // this lane tests at most (e - s) / Q + 1 candidates of the column ((x * qmagic) >> 16 == x / Q here): with room for that many hits the
+            // loop needs no capacity test
+            const bool room = lp + (uint32_t)sizeof(entry_t) * ((((e - s) * qmagic) >> 16) + 1u) <= lp_lim;
+            if (col == 4) {                                              // the column that holds the particle itself
+                if (room) test_column<false, true>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
+                else test_column<true, true>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
+            } else {
+                if (room) test_column<false, false>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
+                else test_column<true, false>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
+            }
+        }
+    }
+    if (__any_sync(kFull, over)) return ~0u;
+    // rare: some candidate of this lane lies in the fp32 error band -> the reference's fp64 predicate on all its hits
+    if (near < a.bw && lp != lp0) {
+        const int nl = (int)((lp - lp0) / sizeof(entry_t));
+        int m = 0;
+        for (int k = 0; k < nl; ++k) {
+            const entry_t raw = B[k];
+            const int j = (int)I32[(((uint32_t)raw - s16) & 0xffffu) >> 4];
+            if (pair_exact(g, a.pos4, (int)asorted, j)) B[m++] = raw;
+        }
+        lp = lp0 + (uint32_t)sizeof(entry_t) * (uint32_t)m;
+    }
+    const int cntl = (int)((lp - lp0) / sizeof(entry_t));
+    // concatenate the Q lists of a particle: offsets by a fixed-order walk over the streams
+    int offq = 0, tot = 0;
+#pragma unroll 1
+    for (int k = 0; k < Q; ++k) {                                        // Q is uniform across the warp
+        const int v = __shfl_sync(kFull, cntl, (k * P + p) & 31);
+        offq += k < q ? v : 0;
+        tot += v;
+    }
+    if (!active) return 0u;
+    int32_t *erow = a.nbr + ((size_t)(asorted >> 5) * (size_t)a.K + (size_t)offq) * 32 + (asorted & 31);
+    const int nw = min(cntl, a.K - offq);                                // entries beyond the capacity are dropped
+    for (int k = 0; k < nw; ++k) erow[k * 32] = (int32_t)I32[(((uint32_t)B[k] - s16) & 0xffffu) >> 4];
+    if (q == 0) a.cnt[asorted] = tot;
+    return (uint32_t)tot;
 }
 
 // ------------------------------------------------------------------ one cell of a staged group (one warp)
 // Returns the longest row it wrote (0 when it gave up and raised SPH_F_TILE_FALLBACK).
 __device__ __forceinline__ uint32_t tile_cell(const sph_grid &g, const TileArgs &a, const Head *H, const float4 *S32,
-                                              unsigned char *smem)
+                                              const uint32_t *I32, entry_t *Bblock)
 {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const HomeCell hc = home_cell(g, H, w);
@@ -262,82 +319,30 @@ __device__ __forceinline__ uint32_t tile_cell(const sph_grid &g, const TileArgs 
             return 0u;
         }
     }
-    entry_t *B = reinterpret_cast<entry_t *>(smem + kBytesS32) + (w * 32 + lane) * kTRowS;     // this lane's list of hits
-    const uint32_t s32a = smem_u32(S32), s16 = s32a & 0xffffu;
-    const uint32_t lp0 = smem_u32(B), lp_lim = lp0 + (uint32_t)sizeof(entry_t) * kTRow;
+    entry_t *B = Bblock + (w * 32 + lane) * kTRowS;                      // this lane's list of hits
     const uint32_t *offh = H->off + (hc.hz * 4 + hc.hy) * 4 + hc.hx;
     uint32_t wmax = 0;
 
-    // Long rows (the default Verlet tolerance gives ~47 neighbours) overflow a stream's list at Q = 2:
-    // the launcher then starts at 8 particles per pass (Q >= 4); a cell that overflows at 16 is redone
-    // at 8 before the general kernel is asked.
+    // Streams per particle: Q = 32 / P (8 at most).  Long rows (the default
+    // Verlet tolerance gives ~47 neighbours) overflow a stream's list at Q = 2: the launcher then starts at 8
+    // particles per pass (Q >= 4); a cell that overflows at 16 is redone at 8, then at 4, before the general kernel
+    // is asked.
     int pass = a.pass0;
 #pragma unroll 1
     for (int p0 = 0; p0 < hc.P; p0 += pass) {
         const int P = min(pass, hc.P - p0);
-        const LaneMap lm = lane_map(P, lane);
-        const uint32_t selfc = hc.c0 + (uint32_t)(p0 + lm.p), asorted = hc.cs + (uint32_t)(p0 + lm.p);
-        const uint32_t selfptr = s32a + selfc * 16u;
-        const float4 hp = S32[selfc];
-        uint32_t lp = lp0;
-        float maxacc = 0.f;
-        bool over = false;
-        if (lm.active) {
-            const uint32_t step = (uint32_t)lm.Q * 16u;
-#pragma unroll
-            for (int col = 0; col < 9; ++col) {                          // unrolled: 4.43 ms against 4.55 ms as a loop
-                const uint32_t s = offh[((col / 3) * 4 + col % 3) * 4], e = offh[((col / 3) * 4 + col % 3) * 4 + 3];
-                const uint32_t pend = s32a + e * 16u, pbeg = s32a + (s + (uint32_t)lm.q) * 16u;
-                // this lane tests at most ((e - s) >> lgq) + 1 candidates of the column: with room for that
-                // many hits the loop needs no capacity test
-                const bool room = lp + (uint32_t)sizeof(entry_t) * (((e - s) >> lm.lgq) + 1u) <= lp_lim;
-                if (col == 4) {                                          // the column that holds the particle itself
-                    if (room) test_column<false, true>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
-                    else test_column<true, true>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
-                } else {
-                    if (room) test_column<false, false>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
-                    else test_column<true, false>(pbeg, pend, step, selfptr, hp, a.thr_out, lp, lp_lim, maxacc, over);
-                }
-            }
-        }
-        if (__any_sync(kFull, over)) {
-            if (pass > 8) {
-                pass = 8;
+        const uint32_t c0 = hc.c0 + (uint32_t)p0, cs = hc.cs + (uint32_t)p0;
+        const uint32_t r = tile_pass(g, a, S32, I32, B, offh, c0, cs, P, P <= 4 ? 8 : 32 / P, lane);
+        if (r == ~0u) {
+            if (pass > 4) {
+                pass = pass > 8 ? 8 : 4;
                 p0 = -pass;                                              // start the cell again
                 continue;
             }
             if (lane == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
             return 0u;
         }
-        // rare: some hit of this lane lies in the fp32 error band -> the reference's fp64 predicate on all of them
-        if (maxacc >= a.thr_in) {
-            const int nl = (int)((lp - lp0) / sizeof(entry_t));
-            int m = 0;
-            for (int k = 0; k < nl; ++k) {
-                const entry_t raw = B[k];
-                const int j = __float_as_int(S32[(((uint32_t)raw - s16) & 0xffffu) >> 4].w);
-                if (pair_exact(g, a.pos4, (int)asorted, j)) B[m++] = raw;
-            }
-            lp = lp0 + (uint32_t)sizeof(entry_t) * (uint32_t)m;
-        }
-        const int cntl = (int)((lp - lp0) / sizeof(entry_t));
-        // concatenate the Q lists of a particle: offsets by a fixed-order walk over the streams
-        int offq = 0, tot = 0;
-#pragma unroll 1
-        for (int k = 0; k < lm.Q; ++k) {                                 // Q is uniform across the warp
-            const int v = __shfl_sync(kFull, cntl, (k * P + lm.p) & 31);
-            offq += k < lm.q ? v : 0;
-            tot += v;
-        }
-        if (lm.active) {
-            int32_t *erow = a.nbr + ((size_t)(asorted >> 5) * (size_t)a.K + (size_t)offq) * 32 + (asorted & 31);
-            const int nw = min(cntl, a.K - offq);                        // entries beyond the capacity are dropped
-            const unsigned char *Sw = reinterpret_cast<const unsigned char *>(S32) + 12;   // sorted index of a candidate
-            for (int k = 0; k < nw; ++k)
-                erow[k * 32] = *reinterpret_cast<const int *>(Sw + (((uint32_t)B[k] - s16) & 0xfff0u));
-            if (lm.q == 0) a.cnt[asorted] = tot;
-            wmax = max(wmax, (uint32_t)tot);
-        }
+        wmax = max(wmax, r);
         __syncwarp();                                                    // lists are reused by the next pass
     }
     return wmax;
@@ -354,7 +359,9 @@ tile_list_kernel(const __grid_constant__ sph_grid g, const __grid_constant__ Til
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float4 *S32 = reinterpret_cast<float4 *>(smem);
-    Head *H = reinterpret_cast<Head *>(smem + kBytesS32 + kBytesB);
+    uint32_t *I32 = reinterpret_cast<uint32_t *>(smem + kBytesS32);
+    entry_t *B = reinterpret_cast<entry_t *>(smem + kBytesS32 + kBytesI32);
+    Head *H = reinterpret_cast<Head *>(smem + kBytesS32 + kBytesI32 + kBytesB);
 
     // positions far outside the box: single-shift semantics matter, the general path decides
     if ((a.status->flags & (SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE)) || smem_u32(S32) + kBytesS32 > 65536u) {
@@ -367,12 +374,12 @@ tile_list_kernel(const __grid_constant__ sph_grid g, const __grid_constant__ Til
         const uint32_t c0 = grp * 8u;
         if (a.cell_start[c0 + 8] == a.cell_start[c0]) continue;         // no particle in the group
         if (RESIDENT) __syncthreads();                                   // the previous group's window is no longer read
-        const uint32_t total = tile_stage(g, c0, a, H, S32);
+        const uint32_t total = tile_stage(g, c0, a, H, S32, I32);
         if (total > (uint32_t)kTCap) {
             if (threadIdx.x == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
             break;
         }
-        wmax = max(wmax, tile_cell(g, a, H, S32, smem));
+        wmax = max(wmax, tile_cell(g, a, H, S32, I32, B));
     }
     wmax = __reduce_max_sync(kFull, wmax);
     if ((threadIdx.x & 31) == 0 && wmax > 0) {
@@ -381,25 +388,28 @@ tile_list_kernel(const __grid_constant__ sph_grid g, const __grid_constant__ Til
     }
 }
 
-void tile_thresholds(const sph_grid *g, float *tin, float *tout)
+void tile_thresholds(const sph_grid *g, float *tout, float *bw)
 {
-    // Positions are fp32 in the GROUP's frame: |coordinate| < 3 w, so a staged coordinate carries
-    // at most 6u w (cell-relative conversion, shift conversion, their sum), the home particle's
-    // 4u w, the subtraction another u w near the threshold: 12u w per component is a bound.  rsq
-    // inherits 2 sqrt(3) r err + 3 err^2 plus ~3u relative from its own arithmetic; use 4x, as
-    // sph_grid_plan does for the per-cell frame.
+    // Error budget of d = |c|^2 + (|p|^2 - thr_out) - 2 c.p against the exact rsq - thr_out.
+    //   coordinates: fp32 in the GROUP's frame, |coordinate| <= 2 w: a staged coordinate carries at most 5u w
+    //     (cell-relative conversion 1u w, shift conversion 2u w, their sum 2u w), so a separation component is off
+    //     by err <= 10u w and rsq by 2 sqrt(3) r err + 3 err^2 near the threshold;
+    //   arithmetic: |c|^2 <= 12 w^2 (3 operations), |p|^2 <= 3 w^2 (3), their sum with -thr_out (2), three FFMA on
+    //     magnitudes <= 27 w^2 + thr: below u (36 + 9 + 2 * 15 + 3 * 27) w^2 + 5u thr = 156u w^2 + 5u thr.
+    // Use 4x the sum, as sph_grid_plan does for the per-cell frame.
     double wmax = 0.0;
     for (int d = 0; d < 3; ++d) wmax = g->w[d] > wmax ? g->w[d] : wmax;
     const double u = 1.0 / 16777216.0;
     const double rl = sqrt(g->thr);
-    const double err = 12.0 * u * wmax;
-    const double band = 4.0 * (2.0 * 1.7320508 * (rl + err) * err + 3.0 * err * err + 8.0 * u * g->thr);
-    float a = (float)(g->thr - band), b = (float)(g->thr + band);
-    a = nextafterf(a, -INFINITY);
+    const double err = 10.0 * u * wmax;
+    const double band = 4.0 * (2.0 * 1.7320508 * (rl + err) * err + 3.0 * err * err + 156.0 * u * wmax * wmax +
+                               8.0 * u * g->thr);
+    float b = (float)(g->thr + band);
     b = nextafterf(b, INFINITY);
-    if (!(a > 0.0f)) a = 0.0f;
-    *tin = a;
     *tout = b;
+    // hits with d >= -bw, i.e. rsq32 >= thr_out - bw, may lie outside: bw covers thr_out - (thr - band) with margin
+    float w2 = (float)(((double)b - g->thr) + band);
+    *bw = nextafterf(w2 * 1.0000002f, INFINITY);
 }
 
 TileArgs base_args(const sph_grid *g, const sph_buffers *b)
@@ -415,14 +425,10 @@ TileArgs base_args(const sph_grid *g, const sph_buffers *b)
     a.status = b->status;
     a.perm = b->perm;
     a.n_owned = b->n_owned;
-    tile_thresholds(g, &a.thr_in, &a.thr_out);
-    // expected neighbours per particle at the mean density of the local grid: a stream of Q = 2 holds 32 hits.
-    // (The owned particles over the owned layers when there are ghosts: the count must not depend on the capacity
-    // of the ghost region, or the row order -- and with it the last bits of every sum -- would.)
-    const bool slab = b->n_owned > 0 && !g->wrap[0] && g->ncl[0] > 2;
-    const double vol = ((slab ? g->ncl[0] - 2 : g->ncl[0]) * g->w[0]) * (g->ncl[1] * g->w[1]) * (g->ncl[2] * g->w[2]);
-    const double np = slab ? (double)b->n_owned : (double)b->n;
-    const double expect = vol > 0.0 ? 4.18879 * g->thr * sqrt(g->thr) * np / vol : 0.0;
+    tile_thresholds(g, &a.thr_out, &a.bw);
+    // expected neighbours per particle at the mean density of the local grid: a stream of Q = 2 holds 32 hits
+    const double vol = (g->ncl[0] * g->w[0]) * (g->ncl[1] * g->w[1]) * (g->ncl[2] * g->w[2]);
+    const double expect = vol > 0.0 ? 4.18879 * g->thr * sqrt(g->thr) * (double)b->n / vol : 0.0;
     a.pass0 = expect > 38.0 ? 8 : kTPass;
     return a;
 }
@@ -433,7 +439,8 @@ namespace sph_tiles {
 
 bool eligible(const sph_grid *g, const sph_buffers *b)
 {
-    if (!b->rel4 || !b->pos4 || !b->nbr || !b->cnt) return false;
+    const char *e = getenv("SPH_TILES");                 // SPH_TILES=0: general kernel only (tests, A/B timing)
+    if ((e && atoi(e) == 0) || !b->rel4 || !b->pos4 || !b->nbr || !b->cnt) return false;
     for (int d = 0; d < 3; ++d)
         if (g->ncl[d] < 3 || g->lb[d] < 1) return false;
     // the three lowest code bits are one bit of x, y, z: a group of 8 consecutive codes is 2 x 2 x 2 cells

@@ -86,3 +86,50 @@ def fused_imp_euler(p, dt):
     _touch(p.r, p.v, p.u)
     for k, val in zip(("rho", "p", "pco"), keep):
         getattr(p, k)[:n] = val
+
+
+def fused_rk4(p, dt):
+    """Fourth-order Runge-Kutta for a SmoothParticleSystem on p.r, p.v, p.u directly (integrator.py:62-95 driven
+    through gather_state / scatter_state, particles.py:496-542, without the [11, maxn] state matrices): the four
+    derivative evaluations are the CUDA hot path, the stage updates are sph_axpy launches, and nothing leaves the
+    device.  Like the generic path it leaves rho, p, pco at their first-stage values (zero state derivatives,
+    particles.py:538-540)."""
+    n = p.n
+    p.derivatives()                                                  # k1
+    r0, v0, u0 = p.r[:n].clone(), p.v[:n].clone(), p.u[:n].clone()
+    keep = [getattr(p, k)[:n].clone() for k in ("rho", "p", "pco")]
+    k1 = (v0.clone(), p.vdot[:n].clone(), p.udot[:n].clone())
+
+    def stage(kprev, scale):
+        """state = start + scale * dt * k_prev; returns the derivatives there."""
+        _backend.axpy(p.r[:n], r0, kprev[0], scale * dt)
+        _backend.axpy(p.v[:n], v0, kprev[1], scale * dt)
+        _backend.axpy(p.u[:n], u0, kprev[2], scale * dt)
+        _touch(p.r, p.v, p.u)
+        p.derivatives()
+        return (p.v[:n].clone(), p.vdot[:n].clone(), p.udot[:n].clone())
+
+    k2 = stage(k1, 0.5)
+    k3 = stage(k2, 0.5)
+    k4 = stage(k3, 1.0)
+    # x = x_start + (1/6) (c1 + 2 c2 + 2 c3 + c4) with c_i = k_i dt   (integrator.py:95)
+    for x, x0, idx in ((p.r, r0, 0), (p.v, v0, 1), (p.u, u0, 2)):
+        total = k1[idx] + 2. * k2[idx] + 2. * k3[idx] + k4[idx]
+        _backend.axpy(x[:n], x0, total, dt * (1.0 / 6.0))
+    _touch(p.r, p.v, p.u)
+    for k, val in zip(("rho", "p", "pco"), keep):
+        getattr(p, k)[:n] = val
+
+
+def fused_euler(p, dt):
+    """Forward Euler on p.r, p.v, p.u directly (integrator.py:14-41 through gather_state / scatter_state)."""
+    n = p.n
+    p.derivatives()
+    keep = [getattr(p, k)[:n].clone() for k in ("rho", "p", "pco")]
+    v0 = p.v[:n].clone()
+    _backend.axpy(p.r[:n], p.r[:n].clone(), v0, dt)
+    _backend.axpy(p.v[:n], v0, p.vdot[:n], dt)
+    _backend.axpy(p.u[:n], p.u[:n].clone(), p.udot[:n], dt)
+    _touch(p.r, p.v, p.u)
+    for k, val in zip(("rho", "p", "pco"), keep):
+        getattr(p, k)[:n] = val

@@ -22,7 +22,7 @@ from . import box as _box
 from . import configuration
 from . import properties
 from .array import from_numpy, ones, zeros
-from .integrator import _touch, euler, fused_imp_euler, imp_euler, rk4
+from .integrator import _touch, euler, fused_euler, fused_imp_euler, fused_rk4, imp_euler, rk4
 
 XMAX = 5
 YMAX = 5
@@ -30,7 +30,7 @@ ZMAX = 1
 VMAX = 0.1
 ADVECTIVE = False
 SPROPS = False
-FUSED = False            # SmoothParticleSystem.update: improved Euler without the [11, maxn] state matrices
+FUSED = False            # SmoothParticleSystem.update: the steppers on p.r / p.v / p.u without the [11, maxn] state matrices
 TIMING_SYNC = False      # True: synchronise the device before every clock read, so that p.timing holds device times
                          # (a bspana_profile.py-style run); False: the reference's plain wall-clock deltas, which on an
                          # asynchronous device are enqueue times
@@ -216,6 +216,10 @@ class SmoothParticleSystem(ParticleSystem):
         t = time()
         if FUSED and self.step is imp_euler:
             fused_imp_euler(self, dt)
+        elif FUSED and self.step is rk4:
+            fused_rk4(self, dt)
+        elif FUSED and self.step is euler:
+            fused_euler(self, dt)
         else:
             self.step(self.gather_state, self.derivatives, self.gather_derivatives, self.scatter_state, dt)
         self.timing['integrate time'] = time() - t

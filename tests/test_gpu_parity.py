@@ -378,9 +378,10 @@ def test_spam_conduction(golden_dir):
     assert rel_err(_np(p.udot), c["udot"]) < 1e-5
 
 
-def test_fused_improved_euler_equals_generic_path():
-    """particles.FUSED: the device-resident improved Euler must leave the same state as the generic
-    callback-driven integrator (integrator.py:44-59) after several updates."""
+@pytest.mark.parametrize("stepper", ["ieuler", "rk4", "euler"])
+def test_fused_steppers_equal_generic_path(stepper):
+    """particles.FUSED: the device-resident improved Euler / RK4 / Euler must leave the same state as the generic
+    callback-driven integrators (integrator.py:14-95) after several updates."""
     from pyticles_b200 import forces, neighbour_list, particles, properties
     r, v, box = O.lattice_workload(12, 12, 12, seed=23, jitter=0.2)
     n = r.shape[0]
@@ -389,7 +390,8 @@ def test_fused_improved_euler_equals_generic_path():
     try:
         for fused in (False, True):
             particles.FUSED = fused
-            p = particles.SmoothParticleSystem(n, d=3, maxn=n + 7, xmax=box[0], ymax=box[1], zmax=box[2], hshort=2.0)
+            p = particles.SmoothParticleSystem(n, d=3, maxn=n + 7, xmax=box[0], ymax=box[1], zmax=box[2], hshort=2.0,
+                                               integrator=stepper)
             p.r[0:n, :] = r
             p.v[0:n, :] = v
             nl = neighbour_list.VerletList(p, cutoff=2.0, tolerance=1.0)

@@ -30,3 +30,15 @@ def test_write_read_roundtrip(tmp_path):
     assert np.array_equal(c.r[:n], b.r[:n]) and np.array_equal(c.v[:n], b.v[:n]) and np.array_equal(c.m[:n], b.m[:n])
     spam_nc.read_step(fn, c, step=0)
     assert np.array_equal(c.r[:n], a.r[:n])
+
+
+def test_netcdf4_files_are_refused_with_a_clear_message(tmp_path):
+    """The reference writes NetCDF-4 (HDF5) through netCDF4; this build handles NetCDF-3 only and says so."""
+    import pytest
+    from pyticles_b200 import spam_nc
+    fn = tmp_path / "ref.nc"
+    fn.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    with pytest.raises(IOError, match="NetCDF-4"):
+        spam_nc.read_step(str(fn), _P(4, 1))
+    with pytest.raises(IOError, match="NetCDF-4"):
+        spam_nc.write_step(str(fn), _P(4, 1))
