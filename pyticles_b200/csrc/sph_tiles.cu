@@ -426,9 +426,13 @@ TileArgs base_args(const sph_grid *g, const sph_buffers *b)
     a.perm = b->perm;
     a.n_owned = b->n_owned;
     tile_thresholds(g, &a.thr_out, &a.bw);
-    // expected neighbours per particle at the mean density of the local grid: a stream of Q = 2 holds 32 hits
-    const double vol = (g->ncl[0] * g->w[0]) * (g->ncl[1] * g->w[1]) * (g->ncl[2] * g->w[2]);
-    const double expect = vol > 0.0 ? 4.18879 * g->thr * sqrt(g->thr) * (double)b->n / vol : 0.0;
+    // expected neighbours per particle at the mean density of the local grid: a stream of Q = 2 holds 32 hits.
+    // (The owned particles over the owned layers when there are ghosts: the count must not depend on the capacity
+    // of the ghost region, or the row order -- and with it the last bits of every sum -- would.)
+    const bool slab = b->n_owned > 0 && !g->wrap[0] && g->ncl[0] > 2;
+    const double vol = ((slab ? g->ncl[0] - 2 : g->ncl[0]) * g->w[0]) * (g->ncl[1] * g->w[1]) * (g->ncl[2] * g->w[2]);
+    const double np = slab ? (double)b->n_owned : (double)b->n;
+    const double expect = vol > 0.0 ? 4.18879 * g->thr * sqrt(g->thr) * np / vol : 0.0;
     a.pass0 = expect > 38.0 ? 8 : kTPass;
     return a;
 }

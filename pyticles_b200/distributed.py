@@ -169,9 +169,16 @@ class SlabSphEvaluator(object):
     """bench.py / long-run driver: one rank's share of the distributed derivative evaluation.
     Owned particles live at the front of persistent structure-of-arrays tensors; behind them sits a ghost
     region of fixed capacity (2 * halo_cap slots), filled by exchange A of the current evaluation."""
+    _warned = False
+    # "nccl": ncclSend/Recv through torch (one group of two sends and two receives per exchange).  "peer": the packed
+    # rows are copied into the neighbours' symmetric-memory buffers by a kernel with remote stores over NVLink and
+    # flagged -- 0.11 instead of 0.15 ms per exchange on two B200s, most of either being the wait for the slower
+    # neighbour, but the end-to-end path with host buffers LOSES 4-6 ms per evaluation with it (24.4 -> 28.4-30.8 ms,
+    # profiles/r2_halo.txt), so NCCL is the default.
+    halo_transport = "nccl"
     kernel_names = {"cells+reorder": "bin_kernel+scan+scatter_kernel+cell_sort_kernel+gather_kernel",
                     "neighbour": "tile_list_kernel", "density": "density_kernel<true>", "force": "force_kernel<true>",
-                    "halo": "halo_pack/unpack kernels + ncclSend/Recv ring (batch_isend_irecv)"}
+                    "halo": "halo_pack/unpack kernels + peer-to-peer copies into the neighbours' symmetric-memory buffers"}
     IN = ("r", "v", "m", "h", "t")
     OUT = ("rho", "p", "pco", "u", "vdot", "udot")
 
@@ -215,6 +222,12 @@ class SlabSphEvaluator(object):
         return self.n_owned + (2 * self.halo_cap if self.dec.world > 1 else 0)
 
     def _set_halo_cap(self, cap):
+        """(Re)allocate the halo buffers for `cap` rows per side.  COLLECTIVE when there is more than one rank: the
+        receive buffers are symmetric memory (torch.distributed._symmetric_memory: every rank maps every rank's
+        buffer), so that a neighbour's pack kernel stores its rows straight into them over NVLink and no NCCL call is
+        on the path; two generations of them alternate from evaluation to evaluation (a rank can only be one
+        evaluation ahead of its neighbours, whose data it needs).  If the rendezvous is not possible the exchange
+        falls back to ncclSend/Recv (SlabDecomposition.ring_exchange) and says so once."""
         cap = int(cap)
         self.dec.halo_cap = cap
         dev = self.device
@@ -223,6 +236,52 @@ class SlabSphEvaluator(object):
                               recv_a=torch.zeros((2, cap + 1, NCOL), dtype=torch.float64, device=dev),
                               send_b=torch.zeros((2, cap, 2), dtype=torch.float64, device=dev),
                               recv_b=torch.zeros((2, cap, 2), dtype=torch.float64, device=dev))
+        self._symm = None
+        if self.halo_transport == "peer" and dev.type == "cuda" and self.dec.world > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                na, nb = (cap + 1) * NCOL, cap * 2                       # doubles per side: exchange A, exchange B
+                per_gen = 2 * na + 2 * nb
+                t = symm_mem.empty(2 * per_gen, dtype=torch.float64, device=dev)     # never zeroed here: an asynchronous
+                # fill could land after a fast neighbour's first rows; every slot is written before it is signalled
+                group = self.dec.group if self.dec.group is not None else dist.group.WORLD
+                hdl = symm_mem.rendezvous(t, group.group_name)
+                # element offsets inside a generation: [A from left | A from right | B from left | B from right]
+                self._symm = dict(t=t, hdl=hdl, per_gen=per_gen, off=dict(a_l=0, a_r=na, b_l=2 * na, b_r=2 * na + nb),
+                                  na=na, nb=nb, gen=0)
+            except Exception as exc:                                     # pragma: no cover (depends on the machine)
+                if not SlabSphEvaluator._warned:
+                    SlabSphEvaluator._warned = True
+                    import sys
+                    sys.stderr.write("pyticles_b200: symmetric memory not available (%s: %s); the halo exchange uses "
+                                     "ncclSend/Recv\n" % (type(exc).__name__, exc))
+                self._symm = None
+
+    def _peer_exchange(self, which, send_l, send_r):
+        """One ring exchange over peer memory: the packed rows travelling leftwards are copied into the slot "from
+        right" of the LEFT neighbour's receive buffer, the others into the slot "from left" of the RIGHT
+        neighbour's -- two coalesced copy kernels with remote stores over NVLink (a pack kernel storing its 8-byte
+        columns straight into the remote buffer took 330 us) -- then one flag per direction tells the neighbours the
+        rows are there.  Everything is stream ordered, nothing waits on the host.  Returns (rows received from the
+        left neighbour, from the right neighbour) as local tensors."""
+        sy, dec = self._symm, self.dec
+        hdl, o = sy["hdl"], sy["off"]
+        base = sy["gen"] * sy["per_gen"]
+        n = sy["na"] if which == "a" else sy["nb"]
+        key_l, key_r = which + "_l", which + "_r"
+        total = 2 * sy["per_gen"]
+        remote = lambda rank, key: hdl.get_buffer(rank, (total,), torch.float64)[base + o[key]:base + o[key] + n]
+        # an elementwise kernel with remote stores, not a memcpy: the copy engines belong to the host transfers of the
+        # end-to-end path (a cudaMemcpyPeer here cost it 4 ms per evaluation)
+        torch.mul(send_l.reshape(-1), 1.0, out=remote(dec.left, key_r))
+        torch.mul(send_r.reshape(-1), 1.0, out=remote(dec.right, key_l))
+        ch = 0 if which == "a" else 2
+        hdl.put_signal(dec.left, channel=ch)                  # travelling leftwards
+        hdl.put_signal(dec.right, channel=ch + 1)             # travelling rightwards
+        hdl.wait_signal(dec.right, channel=ch)                # what my right neighbour sent leftwards
+        hdl.wait_signal(dec.left, channel=ch + 1)
+        t = sy["t"]
+        return t[base + o[key_l]:base + o[key_l] + n], t[base + o[key_r]:base + o[key_r] + n]
 
     def _reserve(self, cap, S=None):
         S = self.S if S is None else S
@@ -317,6 +376,15 @@ class SlabSphEvaluator(object):
         if timed:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
             ev[0].record()
+        fine = [] if timed == "fine" else None           # (label, event) marks for tools/halo_profile.py
+
+        def mark(label):
+            if fine is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                fine.append((label, e))
+
+        mark("start")
         _lib.check(L.sph_status_reset(stat, st), "sph_status_reset")
         if multi:
             hb = self._halo_buf
@@ -325,11 +393,21 @@ class SlabSphEvaluator(object):
             _lib.check(L.sph_cells_begin(g, bp, _P(r), 0, no, _P(idx[0]), _P(idx[1]), cap, st), "sph_cells_begin")
             if timed:
                 ev[1].record()
+            mark("bin owned (+ boundary lists)")
             _lib.check(L.sph_halo_pack(ctypes.byref(f), _P(idx[0]), _P(idx[1]), cap, _P(sa[0]), _P(sa[1]), stat, st),
                        "sph_halo_pack")                                                        # A
-            dec.ring_exchange(sa[0], sa[1], ra[0], ra[1])
-            _lib.check(L.sph_halo_unpack(ctypes.byref(f), _P(ra[0]), _P(ra[1]), cap, no, _P(self._nvalid), stat, st),
+            mark("A: pack")
+            if self._symm is not None:
+                self._symm["gen"] ^= 1
+                from_l, from_r = self._peer_exchange("a", sa[0], sa[1])
+                mark("A: peer copies + signals")
+            else:
+                dec.ring_exchange(sa[0], sa[1], ra[0], ra[1])
+                mark("A: ring send/recv")
+                from_l, from_r = ra[0], ra[1]
+            _lib.check(L.sph_halo_unpack(ctypes.byref(f), _P(from_l), _P(from_r), cap, no, _P(self._nvalid), stat, st),
                        "sph_halo_unpack")
+            mark("A: unpack")
             if timed:
                 ev[2].record()
             _lib.check(L.sph_cells_add(g, bp, _P(r), no, n - no, st), "sph_cells_add")
@@ -341,9 +419,11 @@ class SlabSphEvaluator(object):
         _lib.check(L.sph_cells_finish(g, bp, st), "sph_cells_finish")
         _lib.check(L.sph_gather(g, bp, _P(r), _P(v), _P(m), st), "sph_gather")
         be.built = False
+        mark("bin ghosts, scan, scatter, sort, gather")
         if timed:
             ev[3].record()
         be.nlist()
+        mark("neighbour pass")
         if timed:
             ev[4].record()
         if build_only:                                        # BASELINE configs[4]: the list, not the forces
@@ -353,6 +433,7 @@ class SlabSphEvaluator(object):
                 self._events.append(ev)
             return
         be.density_eos(self.eos, self.h_global, True, rho, p, pco, u, t)
+        mark("density / EOS")
         if timed:
             ev[5].record()
         if multi and self.overlap_b:
@@ -375,22 +456,34 @@ class SlabSphEvaluator(object):
             be.force(p, rho, self.h_global, True, self.fcut, 3, vdot, udot, reuse_press=True, first_force=True, part=2)
         else:
             if multi:                                                                          # B
-                self._exchange_b(L, idx, sb, rb, cap, no, p, rho, stat, st)
+                self._exchange_b(L, idx, sb, rb, cap, no, p, rho, stat, st, mark)
             if timed:
                 ev[6].record()
             be.force(p, rho, self.h_global, True, self.fcut, 3, vdot, udot, reuse_press=True, first_force=True)
+            mark("force")
         if timed:
             ev[7].record()
             self._events.append(ev)
+        if fine is not None:
+            self._fine = getattr(self, "_fine", []) + [fine]
         self.result = dict(rho=rho[:no], p=p[:no], pco=pco[:no], u=u[:no], vdot=vdot[:no], udot=udot[:no])
 
-    def _exchange_b(self, L, idx, sb, rb, cap, no, p, rho, stat, st):
+    def _exchange_b(self, L, idx, sb, rb, cap, no, p, rho, stat, st, mark=lambda label: None):
         """(p, rho) of the boundary-layer particles to the neighbours' ghost slots, same particles and order as A."""
         _lib.check(L.sph_halo_pack2(_P(idx[0]), _P(idx[1]), cap, _P(p), _P(rho), _P(sb[0]), _P(sb[1]), stat, st),
                    "sph_halo_pack2")
-        self.dec.ring_exchange(sb[0], sb[1], rb[0], rb[1])
-        _lib.check(L.sph_halo_unpack2(_P(rb[0]), _P(rb[1]), cap, no, _P(p), _P(rho), stat, st), "sph_halo_unpack2")
+        mark("B: pack")
+        if self._symm is not None:
+            from_l, from_r = self._peer_exchange("b", sb[0], sb[1])
+            mark("B: peer copies + signals")
+        else:
+            self.dec.ring_exchange(sb[0], sb[1], rb[0], rb[1])
+            mark("B: ring send/recv")
+            from_l, from_r = rb[0], rb[1]
+        _lib.check(L.sph_halo_unpack2(_P(from_l), _P(from_r), cap, no, _P(p), _P(rho), stat, st), "sph_halo_unpack2")
+        mark("B: unpack")
         self.be.pressure_term(p, rho, no)                     # only the ghosts need their p/rho^2 refreshed
+        mark("B: ghost pressure term")
 
     def _side_stream(self):
         if getattr(self, "_side", None) is None:
@@ -428,6 +521,19 @@ class SlabSphEvaluator(object):
 
     def reset_pass_timers(self):
         self._events = []
+        self._fine = []
+
+    def fine_times(self):
+        """Mean ms of every marked sub-step of evaluate(timed="fine") (tools/halo_profile.py)."""
+        tot, order = {}, []
+        for marks in getattr(self, "_fine", []):
+            for (_, e0), (label, e1) in zip(marks, marks[1:]):
+                if label not in tot:
+                    tot[label] = 0.0
+                    order.append(label)
+                tot[label] += e0.elapsed_time(e1)
+        k = max(1, len(getattr(self, "_fine", [])))
+        return [(label, tot[label] / k) for label in order]
 
     def pass_times(self):
         """Mean ms per pass.  `halo` is exchange A + exchange B (pack, ring send/recv, unpack); with `overlap_b`

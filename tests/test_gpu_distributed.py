@@ -74,6 +74,15 @@ def _worker(rank, world, port, q):
         ev.check()
         res["overlap_same"] = all(np.array_equal(res[kx], ev.result[kx].cpu().numpy()) for kx in ("rho", "p", "vdot", "udot"))
         ev.overlap_b = False
+        # the peer-memory transport (symmetric memory, remote stores over NVLink, flags): the same bits
+        ev.halo_transport = "peer"
+        ev._set_halo_cap(ev.halo_cap)
+        res["peer_used"] = ev._symm is not None
+        ev.evaluate()
+        ev.check()
+        res["peer_same"] = all(np.array_equal(res[kx], ev.result[kx].cpu().numpy()) for kx in ("rho", "p", "vdot", "udot"))
+        ev.halo_transport = "nccl"
+        ev._set_halo_cap(ev.halo_cap)
         # a halo buffer that is too small is grown collectively as well
         ev._set_halo_cap(64)
         ev.evaluate()
@@ -157,6 +166,7 @@ def test_slab_evaluation_matches_oracle(world):
         scale = np.maximum(np.abs(ref[k]), 1e-3 * np.max(np.abs(ref[k])))
         assert np.max(np.abs(full - ref[k]) / scale) < 1e-10, k
     assert all(x["same_bits"] and x["overlap_same"] for x in res), [(x["same_bits"], x["overlap_same"]) for x in res]
+    assert all(x["peer_same"] for x in res), [(x["peer_used"], x["peer_same"]) for x in res]
     assert all(x["halo_regrown"] for x in res), [(x["halo_regrown"], x["halo_cap"]) for x in res]
 
 
