@@ -63,6 +63,7 @@ struct TileArgs {
     sph_status *status;
     float thr_out, bw;       // d = rsq32 - thr_out; hits with d >= -bw are settled in fp64
     int pass0;               // particles of a cell per pass to start with (16 or 8)
+    int dot;                 // 1: dot-product form of the test, 0: difference form (wide cells)
     const int32_t *perm;
     int n_owned;             // > 0: cells of ghosts (original index >= n_owned) get empty rows
 };
@@ -75,7 +76,16 @@ struct Head {
     float shift[12];         // (i - 2) * w[d] at [4 d + i]: fp32 frame shift of window layer i
     uint32_t part[12];       // cell code contribution of window layer i of dimension d at [4 d + i]; ~0u: no such layer
     int gc[4];               // local cell coordinates of the group's base cell
+    unsigned long long mbar; // SPH_TILE_TMA: transaction barrier of the bulk copies of the window
 };
+
+// SPH_TILE_TMA=1 (variant, not the default): the 64 cell segments of the window (8 particles x 16 bytes each,
+// contiguous in the Morton-sorted rel4 array) are brought into shared memory by 64 one-dimensional bulk copies of the
+// TMA unit (cp.async.bulk, SASS UBLKCP) completing on one mbarrier, and shifted into the group's frame IN shared memory
+// afterwards, instead of LDG -> FADD -> STS per particle.  Measured on the 256^3 box: see profiles/r2_tile_experiments.txt.
+#ifndef SPH_TILE_TMA
+#define SPH_TILE_TMA 0
+#endif
 
 constexpr size_t kBytesS32 = sizeof(float4) * kTCap;
 constexpr size_t kBytesI32 = sizeof(uint32_t) * kTCap;
@@ -94,7 +104,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p)
 // S32 = fp32 position in the group's frame + its squared norm, I32 = sorted index.  Returns the number of
 // staged candidates (> kTCap: nothing was staged).
 __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, const TileArgs &a, Head *H,
-                                               float4 *S32, uint32_t *I32)
+                                               float4 *S32, uint32_t *I32, uint32_t phase)
 {
     const int t = threadIdx.x;
     if (t < 12) {
@@ -153,6 +163,41 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
     // warp w stages window cells 8w .. 8w+7, four cells per pass (8 lanes each)
     const int w = t >> 5, lane = t & 31;
     const float4 *rel = reinterpret_cast<const float4 *>(a.rel4);
+#if SPH_TILE_TMA
+    {
+        const uint32_t mbar = smem_u32(&H->mbar);
+        if (t == 0) {
+            // the window was last touched through the generic proxy (the previous group's tests): order it before
+            // the asynchronous writes, then arm the barrier with the bytes to expect
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(total * 16u) : "memory");
+        }
+        __syncthreads();
+        if (t < 64 && H->cnt[t]) {
+            const uint32_t dst = smem_u32(S32 + H->off[t]);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(rel + H->start[t]), "r"(H->cnt[t] * 16u), "r"(mbar) : "memory");
+        }
+        // every thread waits for the phase to complete (parity alternates from group to group)
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(mbar), "r"(phase) : "memory");
+    }
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+        const int wc = w * 8 + pass * 4 + (lane >> 3);
+        const uint32_t st = H->start[wc], cn = H->cnt[wc], dst = H->off[wc];
+        const float fx = H->shift[wc & 3], fy = H->shift[4 + ((wc >> 2) & 3)], fz = H->shift[8 + (wc >> 4)];
+        for (uint32_t k = lane & 7; k < cn; k += 8) {
+            const float4 p = S32[dst + k];
+            const float x = p.x + fx, y = p.y + fy, z = p.z + fz;
+            S32[dst + k] = make_float4(x, y, z, fmaf(z, z, fmaf(y, y, x * x)));
+            I32[dst + k] = st + k;
+        }
+    }
+#else
+    (void)phase;
 #pragma unroll
     for (int pass = 0; pass < 2; ++pass) {
         const int wc = w * 8 + pass * 4 + (lane >> 3);
@@ -165,6 +210,7 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
             I32[dst + k] = st + k;
         }
     }
+#endif
     __syncthreads();
     return total;
 }
@@ -196,12 +242,21 @@ __device__ __forceinline__ HomeCell home_cell(const sph_grid &g, const Head *H, 
 // One candidate against one home particle: d = rsq32 - thr_out in the dot-product form.  A hit (d < 0) is kept as
 // the 16-bit shared address of the staged candidate; the band [-bw, 0) is settled by the caller from `near`.
 // SELF: the column holds the particle itself.
-template <bool CHECK, bool SELF>
+// DOT: the dot-product form, (px2, py2, pz2, Kp) = (-2 p, |p|^2 - thr_out).  Its rounding error grows with the SQUARE of the
+// coordinates, so grids with a cell much wider than the list radius in some dimension (a sheet in a deep box: coarse z
+// cells) take the difference form instead, (px2, py2, pz2, Kp) = (p, -thr_out): three subtractions and three FFMA.
+template <bool DOT, bool CHECK, bool SELF>
 __device__ __forceinline__ void test_one(uint32_t ptr, uint32_t selfptr, float px2, float py2, float pz2, float Kp,
                                          float cx, float cy, float cz, float cn, uint32_t &lp, uint32_t lp_lim,
                                          float &near, bool &over)
 {
-    const float d = fmaf(cz, pz2, fmaf(cy, py2, fmaf(cx, px2, cn + Kp)));
+    float d;
+    if (DOT) {
+        d = fmaf(cz, pz2, fmaf(cy, py2, fmaf(cx, px2, cn + Kp)));
+    } else {
+        const float dx = cx - px2, dy = cy - py2, dz = cz - pz2;
+        d = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, Kp)));
+    }
     near = fminf(near, fabsf(d));
     if (d < 0.f && (!SELF || ptr != selfptr)) {
         if (CHECK && lp >= lp_lim) {
@@ -214,7 +269,7 @@ __device__ __forceinline__ void test_one(uint32_t ptr, uint32_t selfptr, float p
 }
 
 // One candidate stream (every Q-th candidate from ptr on, below pend; step = 16 Q) of one window column, two per trip
-template <bool CHECK, bool SELF>
+template <bool DOT, bool CHECK, bool SELF>
 __device__ __forceinline__ void test_column(uint32_t ptr, uint32_t pend, uint32_t step, uint32_t selfptr, float px2,
                                             float py2, float pz2, float Kp, uint32_t &lp, uint32_t lp_lim, float &near,
                                             bool &over)
@@ -223,12 +278,12 @@ __device__ __forceinline__ void test_column(uint32_t ptr, uint32_t pend, uint32_
     for (; ptr + step < pend; ptr += 2u * step) {                        // two loads in flight
         SPH_LDS4(ax, ay, az, an, ptr);
         SPH_LDS4(bx, by, bz, bn, ptr + step);
-        test_one<CHECK, SELF>(ptr, selfptr, px2, py2, pz2, Kp, ax, ay, az, an, lp, lp_lim, near, over);
-        test_one<CHECK, SELF>(ptr + step, selfptr, px2, py2, pz2, Kp, bx, by, bz, bn, lp, lp_lim, near, over);
+        test_one<DOT, CHECK, SELF>(ptr, selfptr, px2, py2, pz2, Kp, ax, ay, az, an, lp, lp_lim, near, over);
+        test_one<DOT, CHECK, SELF>(ptr + step, selfptr, px2, py2, pz2, Kp, bx, by, bz, bn, lp, lp_lim, near, over);
     }
     if (ptr < pend) {
         SPH_LDS4(ax, ay, az, an, ptr);
-        test_one<CHECK, SELF>(ptr, selfptr, px2, py2, pz2, Kp, ax, ay, az, an, lp, lp_lim, near, over);
+        test_one<DOT, CHECK, SELF>(ptr, selfptr, px2, py2, pz2, Kp, ax, ay, az, an, lp, lp_lim, near, over);
     }
 }
 
@@ -236,6 +291,7 @@ __device__ __forceinline__ void test_column(uint32_t ptr, uint32_t pend, uint32_
 // (particle p, candidate stream q of Q).  Returns the longest row written, or ~0u when a stream's list overflowed.
 // (Compiling the pass per Q makes every stride an immediate and saves 11 % of the instructions, but the four
 // copies of the unrolled column code no longer fit the instruction cache: 4.89 against 4.37 ms, profiles/r2_tile_*.)
+template <bool DOT>
 __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs &a, const float4 *S32,
                                               const uint32_t *I32, entry_t *B, const uint32_t *offh, uint32_t c0,
                                               uint32_t cs, int P, int Q, int lane)
@@ -247,7 +303,8 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
     const uint32_t selfc = c0 + (uint32_t)p, asorted = cs + (uint32_t)p;
     const uint32_t s32a = smem_u32(S32), s16 = s32a & 0xffffu, selfptr = s32a + selfc * 16u;
     const float4 hp = S32[selfc];
-    const float px2 = -2.0f * hp.x, py2 = -2.0f * hp.y, pz2 = -2.0f * hp.z, Kp = hp.w - a.thr_out;
+    const float px2 = DOT ? -2.0f * hp.x : hp.x, py2 = DOT ? -2.0f * hp.y : hp.y, pz2 = DOT ? -2.0f * hp.z : hp.z,
+                Kp = DOT ? hp.w - a.thr_out : -a.thr_out;
     const uint32_t lp0 = smem_u32(B), lp_lim = lp0 + (uint32_t)sizeof(entry_t) * kTRow;
     uint32_t lp = lp0;
     float near = INFINITY;
@@ -261,11 +318,11 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
             // loop needs no capacity test
             const bool room = lp + (uint32_t)sizeof(entry_t) * ((((e - s) * qmagic) >> 16) + 1u) <= lp_lim;
             if (col == 4) {                                              // the column that holds the particle itself
-                if (room) test_column<false, true>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
-                else test_column<true, true>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
+                if (room) test_column<DOT, false, true>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
+                else test_column<DOT, true, true>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
             } else {
-                if (room) test_column<false, false>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
-                else test_column<true, false>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
+                if (room) test_column<DOT, false, false>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
+                else test_column<DOT, true, false>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
             }
         }
     }
@@ -300,6 +357,7 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
 
 // ------------------------------------------------------------------ one cell of a staged group (one warp)
 // Returns the longest row it wrote (0 when it gave up and raised SPH_F_TILE_FALLBACK).
+template <bool DOT>
 __device__ __forceinline__ uint32_t tile_cell(const sph_grid &g, const TileArgs &a, const Head *H, const float4 *S32,
                                               const uint32_t *I32, entry_t *Bblock)
 {
@@ -332,7 +390,7 @@ __device__ __forceinline__ uint32_t tile_cell(const sph_grid &g, const TileArgs 
     for (int p0 = 0; p0 < hc.P; p0 += pass) {
         const int P = min(pass, hc.P - p0);
         const uint32_t c0 = hc.c0 + (uint32_t)p0, cs = hc.cs + (uint32_t)p0;
-        const uint32_t r = tile_pass(g, a, S32, I32, B, offh, c0, cs, P, P <= 4 ? 8 : 32 / P, lane);
+        const uint32_t r = tile_pass<DOT>(g, a, S32, I32, B, offh, c0, cs, P, P <= 4 ? 8 : 32 / P, lane);
         if (r == ~0u) {
             if (pass > 4) {
                 pass = pass > 8 ? 8 : 4;
@@ -353,7 +411,7 @@ __device__ __forceinline__ uint32_t tile_cell(const sph_grid &g, const TileArgs 
 // (the hardware balances them: 4.25 ms against 4.9 ms for resident blocks on 256^3); on a sparse one (a
 // sheet in a deep box leaves most groups empty) a resident set of blocks, so that an empty group costs
 // two loads instead of a block launch (0.71 -> 0.60 ms on the 1024^2 sheet).
-template <bool RESIDENT>
+template <bool RESIDENT, bool DOT>
 __global__ void __launch_bounds__(kTThreads, kTBlocks)
 tile_list_kernel(const __grid_constant__ sph_grid g, const __grid_constant__ TileArgs a)
 {
@@ -368,18 +426,26 @@ tile_list_kernel(const __grid_constant__ sph_grid g, const __grid_constant__ Til
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
         return;
     }
-    uint32_t wmax = 0;
+    uint32_t wmax = 0, phase = 0;
+#if SPH_TILE_TMA
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&H->mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+#endif
     const uint32_t ngroups = g.ncode / 8u;
     for (uint32_t grp = blockIdx.x; grp < ngroups; grp += RESIDENT ? gridDim.x : ngroups) {
         const uint32_t c0 = grp * 8u;
         if (a.cell_start[c0 + 8] == a.cell_start[c0]) continue;         // no particle in the group
         if (RESIDENT) __syncthreads();                                   // the previous group's window is no longer read
-        const uint32_t total = tile_stage(g, c0, a, H, S32, I32);
+        const uint32_t total = tile_stage(g, c0, a, H, S32, I32, phase);
+        if (total <= (uint32_t)kTCap) phase ^= 1u;                       // (SPH_TILE_TMA: one barrier phase per staged window)
         if (total > (uint32_t)kTCap) {
             if (threadIdx.x == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
             break;
         }
-        wmax = max(wmax, tile_cell(g, a, H, S32, I32, B));
+        wmax = max(wmax, tile_cell<DOT>(g, a, H, S32, I32, B));
     }
     wmax = __reduce_max_sync(kFull, wmax);
     if ((threadIdx.x & 31) == 0 && wmax > 0) {
@@ -388,28 +454,35 @@ tile_list_kernel(const __grid_constant__ sph_grid g, const __grid_constant__ Til
     }
 }
 
-void tile_thresholds(const sph_grid *g, float *tout, float *bw)
+// Thresholds of d = rsq32 - thr_out for the two forms of the test; returns whether the dot-product form is used.
+bool tile_thresholds(const sph_grid *g, float *tout, float *bw)
 {
-    // Error budget of d = |c|^2 + (|p|^2 - thr_out) - 2 c.p against the exact rsq - thr_out.
-    //   coordinates: fp32 in the GROUP's frame, |coordinate| <= 2 w: a staged coordinate carries at most 5u w
-    //     (cell-relative conversion 1u w, shift conversion 2u w, their sum 2u w), so a separation component is off
-    //     by err <= 10u w and rsq by 2 sqrt(3) r err + 3 err^2 near the threshold;
-    //   arithmetic: |c|^2 <= 12 w^2 (3 operations), |p|^2 <= 3 w^2 (3), their sum with -thr_out (2), three FFMA on
-    //     magnitudes <= 27 w^2 + thr: below u (36 + 9 + 2 * 15 + 3 * 27) w^2 + 5u thr = 156u w^2 + 5u thr.
+    // Coordinates are fp32 in the GROUP's frame, |coordinate| <= 2 w: a staged coordinate carries at most 5u w
+    // (cell-relative conversion 1u w, shift conversion 2u w, their sum 2u w), so a separation component is off by
+    // err <= 10u w (11u w with the subtraction of the difference form) and rsq by 2 sqrt(3) r err + 3 err^2 near the
+    // threshold.  On top of that the arithmetic of d:
+    //   difference form  d = dx^2 - thr_out + dy^2 + dz^2: three FFMA on magnitudes <= thr near the threshold: 8u thr;
+    //   dot-product form d = |c|^2 + (|p|^2 - thr_out) - 2 c.p: |c|^2 <= 12 w^2 (3 operations), |p|^2 <= 3 w^2 (3),
+    //                    their sum with -thr_out (2), three FFMA on magnitudes <= 27 w^2 + thr: below
+    //                    u (36 + 9 + 2 * 15 + 3 * 27) w^2 + 5u thr = 156u w^2 + 5u thr -- it grows with the SQUARE of the
+    //                    cell width, so it is only used while that stays below a thousandth of the threshold (cells
+    //                    up to five list radii wide; a sheet in a deep box has z cells a hundred radii wide).
     // Use 4x the sum, as sph_grid_plan does for the per-cell frame.
     double wmax = 0.0;
     for (int d = 0; d < 3; ++d) wmax = g->w[d] > wmax ? g->w[d] : wmax;
     const double u = 1.0 / 16777216.0;
     const double rl = sqrt(g->thr);
-    const double err = 10.0 * u * wmax;
-    const double band = 4.0 * (2.0 * 1.7320508 * (rl + err) * err + 3.0 * err * err + 156.0 * u * wmax * wmax +
-                               8.0 * u * g->thr);
+    const double arith_dot = 156.0 * u * wmax * wmax + 5.0 * u * g->thr;
+    const bool dot = 4.0 * arith_dot < 1.0e-3 * g->thr;
+    const double err = (dot ? 10.0 : 11.0) * u * wmax;
+    const double band = 4.0 * (2.0 * 1.7320508 * (rl + err) * err + 3.0 * err * err + (dot ? arith_dot : 8.0 * u * g->thr));
     float b = (float)(g->thr + band);
     b = nextafterf(b, INFINITY);
     *tout = b;
     // hits with d >= -bw, i.e. rsq32 >= thr_out - bw, may lie outside: bw covers thr_out - (thr - band) with margin
     float w2 = (float)(((double)b - g->thr) + band);
     *bw = nextafterf(w2 * 1.0000002f, INFINITY);
+    return dot;
 }
 
 TileArgs base_args(const sph_grid *g, const sph_buffers *b)
@@ -425,7 +498,7 @@ TileArgs base_args(const sph_grid *g, const sph_buffers *b)
     a.status = b->status;
     a.perm = b->perm;
     a.n_owned = b->n_owned;
-    tile_thresholds(g, &a.thr_out, &a.bw);
+    a.dot = tile_thresholds(g, &a.thr_out, &a.bw) ? 1 : 0;
     // expected neighbours per particle at the mean density of the local grid: a stream of Q = 2 holds 32 hits.
     // (The owned particles over the owned layers when there are ghosts: the count must not depend on the capacity
     // of the ghost region, or the row order -- and with it the last bits of every sum -- would.)
@@ -460,8 +533,10 @@ int launch_list(const sph_grid *g, const sph_buffers *b, cudaStream_t s)
     cudaGetDevice(&dev);
     const int slot = dev >= 0 && dev < 64 ? dev : 0;
     if (!configured[slot]) {
-        cudaFuncSetAttribute(tile_list_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList);
-        cudaFuncSetAttribute(tile_list_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList);
+        cudaFuncSetAttribute(tile_list_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList);
+        cudaFuncSetAttribute(tile_list_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList);
+        cudaFuncSetAttribute(tile_list_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList);
+        cudaFuncSetAttribute(tile_list_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemList);
         cudaDeviceGetAttribute(&sm_of[slot], cudaDevAttrMultiProcessorCount, dev);
         if (sm_of[slot] <= 0) sm_of[slot] = 148;
         configured[slot] = true;
@@ -469,8 +544,14 @@ int launch_list(const sph_grid *g, const sph_buffers *b, cudaStream_t s)
     const TileArgs a = base_args(g, b);
     const unsigned groups = g->ncode / 8u, resident = (unsigned)(sm_of[slot] * kTBlocks);
     const bool sparse = (double)b->n < 24.0 * (double)groups;            // fewer than 3 particles per cell on average
-    if (sparse && groups > resident) tile_list_kernel<true><<<resident, kTThreads, kSmemList, s>>>(*g, a);
-    else tile_list_kernel<false><<<groups, kTThreads, kSmemList, s>>>(*g, a);
+    // (one instantiation per form: only the one launched is ever fetched, so the instruction cache sees one copy)
+    if (sparse && groups > resident) {
+        if (a.dot) tile_list_kernel<true, true><<<resident, kTThreads, kSmemList, s>>>(*g, a);
+        else tile_list_kernel<true, false><<<resident, kTThreads, kSmemList, s>>>(*g, a);
+    } else {
+        if (a.dot) tile_list_kernel<false, true><<<groups, kTThreads, kSmemList, s>>>(*g, a);
+        else tile_list_kernel<false, false><<<groups, kTThreads, kSmemList, s>>>(*g, a);
+    }
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPH_OK : (int)e;
 }

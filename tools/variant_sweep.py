@@ -47,6 +47,8 @@ VARIANTS = {
     "w_f_ahead3": _v(W, SPH_IDX_AHEAD_F=3),
     "w_f_ahead4": _v(W, SPH_IDX_AHEAD_F=4),
     "w_f_r64": _v(W, SPH_FORCE_MINB=8),
+    # round 2: window staged by TMA bulk copies (cp.async.bulk + mbarrier) in the cell-group neighbour kernel
+    "tile_tma": ["-DSPH_TILE_TMA=1"],
     # round 2: the tensor-core variant of the neighbour kernel (csrc/sph_tiles_mma.cu; run with SPH_TILES=2)
     "mma_b5": ["-DSPH_TILE_BLOCKS=5"],    # 5 blocks per SM (48 registers, spills), window capacity 1024
 }
