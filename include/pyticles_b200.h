@@ -62,7 +62,8 @@ enum {
 /* Device-resident status block (64 bytes).  Zero it with sph_status_reset before a build. */
 typedef struct sph_status {
     uint32_t flags;
-    uint32_t max_count;          /* largest per-particle neighbour count seen */
+    uint32_t max_count;          /* with SPH_F_NBR_OVERFLOW: the largest per-particle neighbour count (the capacity
+                                  * needed); otherwise a lower bound of it, possibly 0 */
     uint32_t halo_count[2];      /* particles in the left / right boundary cell layer (sph_cells_begin) */
     uint32_t ghost_count[2];     /* ghosts received from the left / right neighbour (sph_halo_unpack) */
     unsigned long long dsq_max_bits; /* ponder_rebuild: max |r_old - r|^2 as ordered bits */

@@ -151,5 +151,71 @@ def hotspots(path, kernel, unit, top=25):
                                                          key[0] if key else "?", key[1] if key else "?", text))
 
 
+def _sass_lines(kernel, unit):
+    """Source line of every SASS instruction of `kernel` in translation unit `unit` of the in-tree library."""
+    import os
+    import re
+    import tempfile
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(here, "pyticles_b200", "libpyticles_b200.so")
+    tmp = tempfile.mkdtemp()
+    subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
+    cubin = [f for f in os.listdir(tmp) if f.startswith(unit + ".") and f.endswith(".cubin")][0]
+    dis = subprocess.run(["nvdisasm", "--print-line-info", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    seq, cur, active = [], None, False
+    for l in dis.split("\n"):
+        if l.startswith(".text."):
+            active = kernel in l
+            continue
+        if not active:
+            continue
+        m = re.match(r'\s*//## File "([^"]+)", line (\d+)', l)
+        if m:
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            continue
+        if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+.*?;", l):
+            seq.append(cur)
+    return here, seq
+
+
+def stalls(path, kernel, unit, top=25):
+    """Warp-state samples per source line of one kernel, with the three largest stall reasons of each line: where the
+    warps WAIT (hotspots says where they execute).  `kernel` is the mangled-name fragment that selects the function in the
+    library's SASS (e.g. tile_list_kernelILb0ELb1E), `unit` the translation unit (sph_tiles)."""
+    import os
+    here, seq = _sass_lines(kernel, unit)
+    raw = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    start = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    blocks = [(rows[a][1], rows[a + 1], rows[a + 2:b]) for a, b in zip(start, start[1:] + [len(rows)])]
+    name, hdr, data = blocks[0]
+    if len(seq) != len(data):
+        print("# instruction counts differ (%d vs %d): the library is not the profiled build" % (len(seq), len(data)))
+    isamp = hdr.index("# Samples")
+    reasons = [(i, h) for i, h in enumerate(hdr) if h.startswith("stall_") and "(" not in h]
+    agg = collections.defaultdict(lambda: [0, collections.Counter()])
+    tot, totr = 0, collections.Counter()
+    for cur, r in zip(seq, data):
+        n = int(r[isamp] or 0)
+        agg[cur][0] += n
+        tot += n
+        for i, h in reasons:
+            v = int(r[i] or 0)
+            agg[cur][1][h] += v
+            totr[h] += v
+    print("# %s: %d warp samples; by reason: %s" % (name.split("(")[0], tot, ", ".join(
+        "%s %.1f%%" % (h[6:], 100.0 * v / max(tot, 1)) for h, v in totr.most_common(8))))
+    src = {}
+    for key, (n, c) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(top)]:
+        text = ""
+        if key and key[0].endswith((".cu", ".cuh")):
+            fn = os.path.join(here, "pyticles_b200", "csrc", key[0])
+            if os.path.exists(fn):
+                src.setdefault(fn, open(fn).read().split("\n"))
+                text = src[fn][key[1] - 1].strip()[:90]
+        why = " ".join("%s %.0f%%" % (h[6:], 100.0 * v / max(n, 1)) for h, v in c.most_common(3))
+        print("%5.1f%%  %-44s %s:%s  %s" % (100.0 * n / max(tot, 1), why, key[0] if key else "?", key[1] if key else "?", text))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernels": kernels, "traffic": traffic, "hotspots": hotspots}[sys.argv[1]](*sys.argv[2:])
+    {"launches": launches, "kernels": kernels, "traffic": traffic, "hotspots": hotspots, "stalls": stalls}[sys.argv[1]](*sys.argv[2:])

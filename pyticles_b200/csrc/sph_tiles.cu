@@ -107,33 +107,36 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
                                                float4 *S32, uint32_t *I32, uint32_t phase)
 {
     const int t = threadIdx.x;
-    if (t < 12) {
-        // The cell code is additive over the dimensions: (block coordinate * block stride) << lbits plus the
-        // in-block Morton bits.  Twelve threads work out the contribution of window layer i = t & 3 of
-        // dimension d = t >> 2; the 64 cell codes are then three table look-ups and two adds each.
-        const int d = t >> 2, i = t & 3;
-        int cc[3];
-        cell_coords(g, c0, cc[0], cc[1], cc[2]);
-        if (t == 0) { H->gc[0] = cc[0]; H->gc[1] = cc[1]; H->gc[2] = cc[2]; }
-        H->shift[t] = (float)((double)(i - 2) * g.w[d]);
-        int c = cc[d] + i - 1;
-        bool ok = true;
-        if (c < 0) {
-            if (g.wrap[d]) c += g.ncl[d]; else ok = false;
-        } else if (c >= g.ncl[d]) {
-            if (g.wrap[d]) c -= g.ncl[d]; else ok = false;
-        }
-        uint32_t part = ~0u;
-        if (ok) {
-            const uint32_t stride = d == 0 ? 1u : (d == 1 ? g.nblk[0] : g.nblk[0] * g.nblk[1]);
-            part = ((((uint32_t)c >> g.lb[d]) * stride) << g.lbits) |
-                   pdep32((uint32_t)c & ((1u << g.lb[d]) - 1u), g.mask[d]);
-        }
-        H->part[t] = part;
-    }
-    __syncthreads();
     if (t < 64) {
-        const uint32_t px = H->part[t & 3], py = H->part[4 + ((t >> 2) & 3)], pz = H->part[8 + (t >> 4)];
+        // The cell code is additive over the dimensions: (block coordinate * block stride) << lbits plus the
+        // in-block Morton bits.  Twelve lanes of each of the first two warps work out the contribution of window
+        // layer i = lane & 3 of dimension d = lane >> 2 (both warps the same table: no barrier between the table
+        // and the look-ups); the 64 cell codes are then three shuffles and two adds each.
+        const int lane = t & 31;
+        uint32_t part = ~0u;
+        if (lane < 12) {
+            const int d = lane >> 2, i = lane & 3;
+            int cc[3];
+            cell_coords(g, c0, cc[0], cc[1], cc[2]);
+            if (t < 12) {
+                if (t == 0) { H->gc[0] = cc[0]; H->gc[1] = cc[1]; H->gc[2] = cc[2]; }
+                H->shift[t] = (float)((double)(i - 2) * g.w[d]);
+            }
+            int c = cc[d] + i - 1;
+            bool ok = true;
+            if (c < 0) {
+                if (g.wrap[d]) c += g.ncl[d]; else ok = false;
+            } else if (c >= g.ncl[d]) {
+                if (g.wrap[d]) c -= g.ncl[d]; else ok = false;
+            }
+            if (ok) {
+                const uint32_t stride = d == 0 ? 1u : (d == 1 ? g.nblk[0] : g.nblk[0] * g.nblk[1]);
+                part = ((((uint32_t)c >> g.lb[d]) * stride) << g.lbits) |
+                       pdep32((uint32_t)c & ((1u << g.lb[d]) - 1u), g.mask[d]);
+            }
+        }
+        const uint32_t px = __shfl_sync(kFull, part, t & 3), py = __shfl_sync(kFull, part, 4 + ((t >> 2) & 3)),
+                       pz = __shfl_sync(kFull, part, 8 + (t >> 4));
         uint32_t st = 0, cn = 0;
         if (px != ~0u && py != ~0u && pz != ~0u) {
             const uint32_t code = px + py + pz;
@@ -155,10 +158,14 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
         const uint32_t ex = inc - (v0 + v1);
         H->off[2 * t] = ex;
         H->off[2 * t + 1] = ex + v0;
-        if (t == 31) H->off[64] = inc;
+        // the group's own cells are window cells 21, 22, 25, 26, 37, 38, 41, 42: is there a particle in any of them?
+        const uint32_t own = ((0x00141400u >> t) & 1u) ? v1 : (((0x00282800u >> t) & 1u) ? v0 : 0u);
+        const bool any = __any_sync(kFull, own != 0u);
+        if (t == 31) { H->off[64] = inc; H->off[65] = any ? 1u : 0u; }
     }
     __syncthreads();
     const uint32_t total = H->off[64];
+    if (H->off[65] == 0u) return 0u;                                     // nothing to do for this group
     if (total > (uint32_t)kTCap) return total;
     // warp w stages window cells 8w .. 8w+7, four cells per pass (8 lanes each)
     const int w = t >> 5, lane = t & 31;
@@ -198,17 +205,42 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
     }
 #else
     (void)phase;
+    {
+        // lane (c, k) = (lane >> 3, lane & 7) takes particles k, k + 8, ... of window cells 8w + c and 8w + 4 + c.  The
+        // first two rows of both cells are requested before any is used (four loads in flight instead of one per loop trip)
+        const uint32_t k0 = lane & 7;
+        uint32_t st[2], cn[2], dst[2];
+        float fx[2], fy[2], fz[2];
+        float4 p[4];
 #pragma unroll
-    for (int pass = 0; pass < 2; ++pass) {
-        const int wc = w * 8 + pass * 4 + (lane >> 3);
-        const uint32_t st = H->start[wc], cn = H->cnt[wc], dst = H->off[wc];
-        const float fx = H->shift[wc & 3], fy = H->shift[4 + ((wc >> 2) & 3)], fz = H->shift[8 + (wc >> 4)];
-        for (uint32_t k = lane & 7; k < cn; k += 8) {
-            const float4 p = __ldg(rel + st + k);
-            const float x = p.x + fx, y = p.y + fy, z = p.z + fz;
-            S32[dst + k] = make_float4(x, y, z, fmaf(z, z, fmaf(y, y, x * x)));
-            I32[dst + k] = st + k;
+        for (int pass = 0; pass < 2; ++pass) {
+            const int wc = w * 8 + pass * 4 + (lane >> 3);
+            st[pass] = H->start[wc]; cn[pass] = H->cnt[wc]; dst[pass] = H->off[wc];
+            fx[pass] = H->shift[wc & 3]; fy[pass] = H->shift[4 + ((wc >> 2) & 3)]; fz[pass] = H->shift[8 + (wc >> 4)];
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t k = k0 + 8u * (uint32_t)(i & 1);
+            if (k < cn[i >> 1]) p[i] = __ldg(rel + st[i >> 1] + k);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = i >> 1;
+            const uint32_t k = k0 + 8u * (uint32_t)(i & 1);
+            if (k < cn[c]) {
+                const float x = p[i].x + fx[c], y = p[i].y + fy[c], z = p[i].z + fz[c];
+                S32[dst[c] + k] = make_float4(x, y, z, fmaf(z, z, fmaf(y, y, x * x)));
+                I32[dst[c] + k] = st[c] + k;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            for (uint32_t k = k0 + 16u; k < cn[c]; k += 8) {             // cells of more than 16 particles
+                const float4 q = __ldg(rel + st[c] + k);
+                const float x = q.x + fx[c], y = q.y + fy[c], z = q.z + fz[c];
+                S32[dst[c] + k] = make_float4(x, y, z, fmaf(z, z, fmaf(y, y, x * x)));
+                I32[dst[c] + k] = st[c] + k;
+            }
     }
 #endif
     __syncthreads();
@@ -328,13 +360,24 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
     }
     if (__any_sync(kFull, over)) return ~0u;
     // rare: some candidate of this lane lies in the fp32 error band -> the reference's fp64 predicate on all its hits
+    // (`near` also sees the misses just above the threshold, which need nothing: so d is worked out again for every hit of
+    // the lane -- the same operations on the same operands give the same bits -- and only hits inside the band pay the
+    // two fp64 rows from global memory)
     if (near < a.bw && lp != lp0) {
         const int nl = (int)((lp - lp0) / sizeof(entry_t));
         int m = 0;
         for (int k = 0; k < nl; ++k) {
             const entry_t raw = B[k];
-            const int j = (int)I32[(((uint32_t)raw - s16) & 0xffffu) >> 4];
-            if (pair_exact(g, a.pos4, (int)asorted, j)) B[m++] = raw;
+            const uint32_t c = (((uint32_t)raw - s16) & 0xffffu) >> 4;
+            const float4 cp = S32[c];
+            float d;
+            if (DOT) {
+                d = fmaf(cp.z, pz2, fmaf(cp.y, py2, fmaf(cp.x, px2, cp.w + Kp)));
+            } else {
+                const float dx = cp.x - px2, dy = cp.y - py2, dz = cp.z - pz2;
+                d = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, Kp)));
+            }
+            if (d < -a.bw || pair_exact(g, a.pos4, (int)asorted, (int)I32[c])) B[m++] = raw;
         }
         lp = lp0 + (uint32_t)sizeof(entry_t) * (uint32_t)m;
     }
@@ -350,7 +393,15 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
     if (!active) return 0u;
     int32_t *erow = a.nbr + ((size_t)(asorted >> 5) * (size_t)a.K + (size_t)offq) * 32 + (asorted & 31);
     const int nw = min(cntl, a.K - offq);                                // entries beyond the capacity are dropped
-    for (int k = 0; k < nw; ++k) erow[k * 32] = (int32_t)I32[(((uint32_t)B[k] - s16) & 0xffffu) >> 4];
+    int k = 0;
+    for (; k + 4 <= nw; k += 4) {                                        // four independent look-up chains in flight
+        const uint32_t b0 = B[k], b1 = B[k + 1], b2 = B[k + 2], b3 = B[k + 3];
+        const uint32_t j0 = I32[((b0 - s16) & 0xffffu) >> 4], j1 = I32[((b1 - s16) & 0xffffu) >> 4],
+                       j2 = I32[((b2 - s16) & 0xffffu) >> 4], j3 = I32[((b3 - s16) & 0xffffu) >> 4];
+        erow[k * 32] = (int32_t)j0; erow[(k + 1) * 32] = (int32_t)j1;
+        erow[(k + 2) * 32] = (int32_t)j2; erow[(k + 3) * 32] = (int32_t)j3;
+    }
+    for (; k < nw; ++k) erow[k * 32] = (int32_t)I32[(((uint32_t)B[k] - s16) & 0xffffu) >> 4];
     if (q == 0) a.cnt[asorted] = tot;
     return (uint32_t)tot;
 }
@@ -421,8 +472,12 @@ tile_list_kernel(const __grid_constant__ sph_grid g, const __grid_constant__ Til
     entry_t *B = reinterpret_cast<entry_t *>(smem + kBytesS32 + kBytesI32);
     Head *H = reinterpret_cast<Head *>(smem + kBytesS32 + kBytesI32 + kBytesB);
 
-    // positions far outside the box: single-shift semantics matter, the general path decides
-    if ((a.status->flags & (SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE)) || smem_u32(S32) + kBytesS32 > 65536u) {
+    // Positions far outside the box: single-shift semantics matter, the general path decides.  A block with one group
+    // of its own does not wait for the flags before it starts (one dependent round trip to L2 less per block: what it
+    // writes is finite garbage in that case and the general kernel behind overwrites every row); block 0 raises the
+    // fallback at the end.
+    if (smem_u32(S32) + kBytesS32 > 65536u ||
+        (RESIDENT && (a.status->flags & (SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE)))) {
         if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
         return;
     }
@@ -437,9 +492,12 @@ tile_list_kernel(const __grid_constant__ sph_grid g, const __grid_constant__ Til
     const uint32_t ngroups = g.ncode / 8u;
     for (uint32_t grp = blockIdx.x; grp < ngroups; grp += RESIDENT ? gridDim.x : ngroups) {
         const uint32_t c0 = grp * 8u;
-        if (a.cell_start[c0 + 8] == a.cell_start[c0]) continue;         // no particle in the group
+        // no particle in the group: a resident block looks before it stages (most groups of a sparse grid are
+        // empty); a block with one group learns it from the window counts, without a round trip of its own
+        if (RESIDENT && a.cell_start[c0 + 8] == a.cell_start[c0]) continue;
         if (RESIDENT) __syncthreads();                                   // the previous group's window is no longer read
         const uint32_t total = tile_stage(g, c0, a, H, S32, I32, phase);
+        if (total == 0u) continue;
         if (total <= (uint32_t)kTCap) phase ^= 1u;                       // (SPH_TILE_TMA: one barrier phase per staged window)
         if (total > (uint32_t)kTCap) {
             if (threadIdx.x == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
@@ -448,10 +506,15 @@ tile_list_kernel(const __grid_constant__ sph_grid g, const __grid_constant__ Til
         wmax = max(wmax, tile_cell<DOT>(g, a, H, S32, I32, B));
     }
     wmax = __reduce_max_sync(kFull, wmax);
-    if ((threadIdx.x & 31) == 0 && wmax > 0) {
-        if (wmax > *(volatile uint32_t *)&a.status->max_count) atomicMax(&a.status->max_count, wmax);
-        if (wmax > (uint32_t)a.K) atomicOr(&a.status->flags, SPH_F_NBR_OVERFLOW);
+    // (only rows longer than the capacity report their length: a look at status->max_count before every warp's exit
+    // is a round trip to L2 during which the block keeps its shared memory)
+    if ((threadIdx.x & 31) == 0 && wmax > (uint32_t)a.K) {
+        atomicMax(&a.status->max_count, wmax);
+        atomicOr(&a.status->flags, SPH_F_NBR_OVERFLOW);
     }
+    if (!RESIDENT && blockIdx.x == 0 && threadIdx.x == 0 &&
+        (*(volatile uint32_t *)&a.status->flags & (SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE)))
+        atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
 }
 
 // Thresholds of d = rsq32 - thr_out for the two forms of the test; returns whether the dot-product form is used.
