@@ -45,7 +45,9 @@ constexpr int kTPass = 16;           // particles of a cell per pass (Q = 32 / P
 constexpr int kTPart = 64;           // particles per cell the tile path handles (cell width ~2 lattice planes: 8 .. 27)
 constexpr int kTRow = 32;            // hits one lane (one stream of one particle) can hold
 typedef uint16_t entry_t;            // a hit is the 16-bit shared address of the staged candidate
-constexpr int kTRowS = 34;           // list stride in shared memory (entries; 17 words: lanes fall in distinct banks)
+constexpr int kTStep = 32 * 2;       // bytes between consecutive hits of a lane: the lists of a warp are interleaved (hit k of lane l at
+                                     // entry 32 k + l), so the lanes of a store fall into distinct banks (or share a word) at ANY mix of
+                                     // list depths -- lists side by side at a 17-word stride cost 2.2 wavefronts per store
 #ifndef SPH_TILE_BLOCKS
 #define SPH_TILE_BLOCKS 5
 #endif
@@ -74,7 +76,6 @@ struct Head {
     uint32_t start[64];      // first sorted particle of window cell (wz*4 + wy)*4 + wx
     uint32_t cnt[64];
     float shift[12];         // (i - 2) * w[d] at [4 d + i]: fp32 frame shift of window layer i
-    uint32_t part[12];       // cell code contribution of window layer i of dimension d at [4 d + i]; ~0u: no such layer
     int gc[4];               // local cell coordinates of the group's base cell
     unsigned long long mbar; // SPH_TILE_TMA: transaction barrier of the bulk copies of the window
 };
@@ -89,7 +90,7 @@ struct Head {
 
 constexpr size_t kBytesS32 = sizeof(float4) * kTCap;
 constexpr size_t kBytesI32 = sizeof(uint32_t) * kTCap;
-constexpr size_t kBytesB = sizeof(entry_t) * kTWarps * 32 * kTRowS;
+constexpr size_t kBytesB = sizeof(entry_t) * kTWarps * 32 * kTRow;
 constexpr size_t kSmemList = kBytesS32 + kBytesI32 + kBytesB + sizeof(Head);
 static_assert(kTBlocks * (kSmemList + 1024) <= 227 * 1024, "blocks per SM");
 static_assert(kBytesS32 + 1024 < 65536, "hits are kept as 16-bit shared addresses of the staged candidate");
@@ -107,22 +108,20 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
                                                float4 *S32, uint32_t *I32, uint32_t phase)
 {
     const int t = threadIdx.x;
-    if (t < 64) {
+    if (t < 32) {
+        // ONE warp fills the head, so that a single barrier stands between the start of the block and the staging of the
+        // window (the table, the look-ups and the scan used to be three phases with a barrier after each: the other
+        // warps of the block spent a fifth of its lifetime waiting at them).
         // The cell code is additive over the dimensions: (block coordinate * block stride) << lbits plus the
-        // in-block Morton bits.  Twelve lanes of each of the first two warps work out the contribution of window
-        // layer i = lane & 3 of dimension d = lane >> 2 (both warps the same table: no barrier between the table
-        // and the look-ups); the 64 cell codes are then three shuffles and two adds each.
-        const int lane = t & 31;
+        // in-block Morton bits.  Lane 4 d + i works out the contribution of window layer i of dimension d;
+        // the 64 cell codes are then three shuffles and two adds each, two cells (2 t, 2 t + 1) per lane.
         uint32_t part = ~0u;
-        if (lane < 12) {
-            const int d = lane >> 2, i = lane & 3;
-            int cc[3];
-            cell_coords(g, c0, cc[0], cc[1], cc[2]);
-            if (t < 12) {
-                if (t == 0) { H->gc[0] = cc[0]; H->gc[1] = cc[1]; H->gc[2] = cc[2]; }
-                H->shift[t] = (float)((double)(i - 2) * g.w[d]);
-            }
-            int c = cc[d] + i - 1;
+        const int d = (t >> 2) % 3, i = t & 3;
+        uint32_t bx, by, bz;
+        block_coords(g, c0 >> g.lbits, bx, by, bz);
+        const int ccd = (int)(((d == 0 ? bx : (d == 1 ? by : bz)) << g.lb[d]) | pext32(c0, g.mask[d]));
+        if (t < 12) {
+            int c = ccd + i - 1;
             bool ok = true;
             if (c < 0) {
                 if (g.wrap[d]) c += g.ncl[d]; else ok = false;
@@ -135,20 +134,25 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
                        pdep32((uint32_t)c & ((1u << g.lb[d]) - 1u), g.mask[d]);
             }
         }
-        const uint32_t px = __shfl_sync(kFull, part, t & 3), py = __shfl_sync(kFull, part, 4 + ((t >> 2) & 3)),
-                       pz = __shfl_sync(kFull, part, 8 + (t >> 4));
-        uint32_t st = 0, cn = 0;
-        if (px != ~0u && py != ~0u && pz != ~0u) {
-            const uint32_t code = px + py + pz;
-            st = a.cell_start[code];
-            cn = a.cell_start[code + 1] - st;
+        uint32_t st[2], cn[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = 2 * t + j;
+            const uint32_t px = __shfl_sync(kFull, part, c & 3), py = __shfl_sync(kFull, part, 4 + ((c >> 2) & 3)),
+                           pz = __shfl_sync(kFull, part, 8 + (c >> 4));
+            st[j] = 0; cn[j] = 0;
+            if (px != ~0u && py != ~0u && pz != ~0u) {
+                const uint32_t code = px + py + pz;
+                st[j] = a.cell_start[code];
+                cn[j] = a.cell_start[code + 1];
+            }
         }
-        H->start[t] = st;
-        H->cnt[t] = cn;
-    }
-    __syncthreads();
-    if (t < 32) {
-        const uint32_t v0 = H->cnt[2 * t], v1 = H->cnt[2 * t + 1];
+        // (while the four loads are in flight)
+        if (t < 12) {
+            if (i == 0) H->gc[d] = ccd;
+            H->shift[t] = (float)((double)(i - 2) * g.w[d]);
+        }
+        const uint32_t v0 = cn[0] - st[0], v1 = cn[1] - st[1];
         uint32_t inc = v0 + v1;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -156,11 +160,12 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
             if (t >= o) inc += x;
         }
         const uint32_t ex = inc - (v0 + v1);
-        H->off[2 * t] = ex;
-        H->off[2 * t + 1] = ex + v0;
         // the group's own cells are window cells 21, 22, 25, 26, 37, 38, 41, 42: is there a particle in any of them?
         const uint32_t own = ((0x00141400u >> t) & 1u) ? v1 : (((0x00282800u >> t) & 1u) ? v0 : 0u);
         const bool any = __any_sync(kFull, own != 0u);
+        *reinterpret_cast<uint2 *>(&H->start[2 * t]) = make_uint2(st[0], st[1]);
+        *reinterpret_cast<uint2 *>(&H->cnt[2 * t]) = make_uint2(v0, v1);
+        *reinterpret_cast<uint2 *>(&H->off[2 * t]) = make_uint2(ex, ex + v0);
         if (t == 31) { H->off[64] = inc; H->off[65] = any ? 1u : 0u; }
     }
     __syncthreads();
@@ -295,7 +300,7 @@ __device__ __forceinline__ void test_one(uint32_t ptr, uint32_t selfptr, float p
             over = true;
         } else {
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(lp), "h"((unsigned short)ptr) : "memory");
-            lp += (uint32_t)sizeof(entry_t);
+            lp += (uint32_t)kTStep;
         }
     }
 }
@@ -337,7 +342,7 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
     const float4 hp = S32[selfc];
     const float px2 = DOT ? -2.0f * hp.x : hp.x, py2 = DOT ? -2.0f * hp.y : hp.y, pz2 = DOT ? -2.0f * hp.z : hp.z,
                 Kp = DOT ? hp.w - a.thr_out : -a.thr_out;
-    const uint32_t lp0 = smem_u32(B), lp_lim = lp0 + (uint32_t)sizeof(entry_t) * kTRow;
+    const uint32_t lp0 = smem_u32(B), lp_lim = lp0 + (uint32_t)kTStep * kTRow;
     uint32_t lp = lp0;
     float near = INFINITY;
     bool over = false;
@@ -348,7 +353,7 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
             const uint32_t pend = s32a + e * 16u, pbeg = s32a + (s + (uint32_t)q) * 16u;
             // this lane tests at most (e - s) / Q + 1 candidates of the column ((x * qmagic) >> 16 == x / Q here): with room for that many hits the
             // loop needs no capacity test
-            const bool room = lp + (uint32_t)sizeof(entry_t) * ((((e - s) * qmagic) >> 16) + 1u) <= lp_lim;
+            const bool room = lp + (uint32_t)kTStep * ((((e - s) * qmagic) >> 16) + 1u) <= lp_lim;
             if (col == 4) {                                              // the column that holds the particle itself
                 if (room) test_column<DOT, false, true>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
                 else test_column<DOT, true, true>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
@@ -364,10 +369,10 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
     // the lane -- the same operations on the same operands give the same bits -- and only hits inside the band pay the
     // two fp64 rows from global memory)
     if (near < a.bw && lp != lp0) {
-        const int nl = (int)((lp - lp0) / sizeof(entry_t));
+        const int nl = (int)((lp - lp0) / (uint32_t)kTStep);
         int m = 0;
         for (int k = 0; k < nl; ++k) {
-            const entry_t raw = B[k];
+            const entry_t raw = B[k * 32];
             const uint32_t c = (((uint32_t)raw - s16) & 0xffffu) >> 4;
             const float4 cp = S32[c];
             float d;
@@ -377,11 +382,11 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
                 const float dx = cp.x - px2, dy = cp.y - py2, dz = cp.z - pz2;
                 d = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, Kp)));
             }
-            if (d < -a.bw || pair_exact(g, a.pos4, (int)asorted, (int)I32[c])) B[m++] = raw;
+            if (d < -a.bw || pair_exact(g, a.pos4, (int)asorted, (int)I32[c])) B[32 * m++] = raw;
         }
-        lp = lp0 + (uint32_t)sizeof(entry_t) * (uint32_t)m;
+        lp = lp0 + (uint32_t)kTStep * (uint32_t)m;
     }
-    const int cntl = (int)((lp - lp0) / sizeof(entry_t));
+    const int cntl = (int)((lp - lp0) / (uint32_t)kTStep);
     // concatenate the Q lists of a particle: offsets by a fixed-order walk over the streams
     int offq = 0, tot = 0;
 #pragma unroll 1
@@ -395,13 +400,13 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
     const int nw = min(cntl, a.K - offq);                                // entries beyond the capacity are dropped
     int k = 0;
     for (; k + 4 <= nw; k += 4) {                                        // four independent look-up chains in flight
-        const uint32_t b0 = B[k], b1 = B[k + 1], b2 = B[k + 2], b3 = B[k + 3];
+        const uint32_t b0 = B[k * 32], b1 = B[k * 32 + 32], b2 = B[k * 32 + 64], b3 = B[k * 32 + 96];
         const uint32_t j0 = I32[((b0 - s16) & 0xffffu) >> 4], j1 = I32[((b1 - s16) & 0xffffu) >> 4],
                        j2 = I32[((b2 - s16) & 0xffffu) >> 4], j3 = I32[((b3 - s16) & 0xffffu) >> 4];
         erow[k * 32] = (int32_t)j0; erow[(k + 1) * 32] = (int32_t)j1;
         erow[(k + 2) * 32] = (int32_t)j2; erow[(k + 3) * 32] = (int32_t)j3;
     }
-    for (; k < nw; ++k) erow[k * 32] = (int32_t)I32[(((uint32_t)B[k] - s16) & 0xffffu) >> 4];
+    for (; k < nw; ++k) erow[k * 32] = (int32_t)I32[(((uint32_t)B[k * 32] - s16) & 0xffffu) >> 4];
     if (q == 0) a.cnt[asorted] = tot;
     return (uint32_t)tot;
 }
@@ -428,7 +433,7 @@ __device__ __forceinline__ uint32_t tile_cell(const sph_grid &g, const TileArgs 
             return 0u;
         }
     }
-    entry_t *B = Bblock + (w * 32 + lane) * kTRowS;                      // this lane's list of hits
+    entry_t *B = Bblock + w * 32 * kTRow + lane;                         // this lane's list of hits: B[32 k]
     const uint32_t *offh = H->off + (hc.hz * 4 + hc.hy) * 4 + hc.hx;
     uint32_t wmax = 0;
 
