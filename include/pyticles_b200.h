@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SPH_ABI_VERSION 3      /* sph_version() reports the same number */
+#define SPH_ABI_VERSION 4      /* sph_version() reports the same number */
 
 enum {
     SPH_OK = 0,
@@ -131,6 +131,11 @@ typedef struct sph_buffers {
                                restricted by sph_grid_restrict_x the ghosts are the particles of the first and the
                                last local x layer; anything else raises SPH_F_OUT_OF_SLAB */
     int32_t reserved0;
+    const uint32_t *group_tab; /* [sph_group_tab_elems(grid)] or NULL: what the neighbour pass needs to know about every
+                               group of 2 x 2 x 2 cells and depends on the GRID only (the cell-code contributions of
+                               the 4 + 4 + 4 cell layers around it, its base cell coordinates), written by
+                               sph_group_table once per grid.  NULL: every block of sph_nlist_build works it out
+                               again (~250 dependent instructions before its first load) */
 } sph_buffers;
 
 /* ------------------------------------------------------------------ host-side planning */
@@ -148,6 +153,10 @@ int sph_grid_restrict_x(sph_grid *grid, int32_t first_layer, int32_t n_layers);
 int64_t sph_scan_tmp_elems(uint32_t ncode);
 /* Elements needed in sph_buffers.nbr. */
 int64_t sph_nbr_elems(int32_t n, int32_t max_nbrs);
+/* Elements (uint32) of sph_buffers.group_tab for this grid; 0 when the grid has no use for one. */
+int64_t sph_group_tab_elems(const sph_grid *grid);
+/* Fill buf->group_tab for `grid` (call again whenever the grid changes, sph_grid_restrict_x included). */
+int sph_group_table(const sph_grid *grid, const sph_buffers *buf, void *stream);
 
 /* ------------------------------------------------------------------ the hot path */
 

@@ -18,7 +18,7 @@ SPH_F_NBR_OVERFLOW = 8
 SPH_F_OUT_OF_SLAB = 16
 SPH_F_TILE_FALLBACK = 32
 SPH_F_HALO_OVERFLOW = 64
-SPH_ABI_VERSION = 3
+SPH_ABI_VERSION = 4
 HALO_COLS = 10
 
 c_double3 = ctypes.c_double * 3
@@ -79,7 +79,8 @@ class SphBuffers(ctypes.Structure):
                 ("n_valid", ctypes.c_void_p),
                 ("sort_key", ctypes.c_void_p),
                 ("n_owned", ctypes.c_int32),
-                ("reserved0", ctypes.c_int32)]
+                ("reserved0", ctypes.c_int32),
+                ("group_tab", ctypes.c_void_p)]
 
 
 class SphFields(ctypes.Structure):
@@ -106,6 +107,8 @@ SIGNATURES = {
     "sph_grid_restrict_x": (ctypes.c_int, [_gp, _i32, _i32]),
     "sph_scan_tmp_elems": (_i64, [ctypes.c_uint32]),
     "sph_nbr_elems": (_i64, [_i32, _i32]),
+    "sph_group_tab_elems": (_i64, [_gp]),
+    "sph_group_table": (ctypes.c_int, [_gp, _bp, _vp]),
     "sph_status_reset": (ctypes.c_int, [_vp, _vp]),
     "sph_cells_build": (ctypes.c_int, [_gp, _bp, _vp, _vp]),
     "sph_cells_begin": (ctypes.c_int, [_gp, _bp, _vp, _i32, _i32, _vp, _vp, _i32, _vp]),

@@ -41,6 +41,7 @@ class NeighbourBackend(object):
         self.t = {}
         self.status_t = torch.zeros(16, dtype=torch.int32, device=self.device)
         self.built = False
+        self._tab_key = None
         self.fresh = False          # sorted positions are the ones the list was built from
         self.press_ready = False    # vel4[.,3] holds press/rho^2 of the last density pass
 
@@ -108,6 +109,17 @@ class NeighbourBackend(object):
         b.nbr = _ptr(self._alloc("nbr", self.lib.sph_nbr_elems(n, self.K), torch.int32))
         b.cnt = _ptr(self._alloc("cnt", n, torch.int32))
         b.status = _ptr(self.status_t)
+        # per-grid table of the cell-group neighbour kernel (geometry only: refilled when the grid changes)
+        elems = int(self.lib.sph_group_tab_elems(ctypes.byref(g)))
+        if elems:
+            old = self.t.get("group_tab")
+            tab = self._alloc("group_tab", elems, torch.int32)
+            b.group_tab = _ptr(tab)
+            if tab is not old or self._tab_key != bytes(g):
+                check(self.lib.sph_group_table(ctypes.byref(g), ctypes.byref(b), _stream()), "sph_group_table")
+                self._tab_key = bytes(g)
+        else:
+            b.group_tab = None
 
     # ------------------------------------------------------------------ the hot path
     def cells_and_gather(self, r, v, m):

@@ -780,6 +780,69 @@ force_kernel(const __grid_constant__ sph_grid g, int n, int K, const double *__r
     }
 }
 
+// The force pass over the particles of a slab's two boundary cell layers ONLY (part 2 of sph_force on a restricted grid):
+// 16 lanes per cell of local x layers 1 and ncl[0] - 2, found through the cell table, so that the launch costs what
+// those 1-2 % of the particles cost -- the flag test of force_kernel walks every warp of the system for them.  This is the
+// launch that waits for the ghosts' (p, rho); everything else runs while they travel (SlabSphEvaluator.overlap_b).
+template <bool UNIFORM_H>
+__global__ void __launch_bounds__(kPPBlock, SPH_FORCE_MINB)
+force_edge_kernel(const __grid_constant__ sph_grid g, int K, const double *__restrict__ pos4,
+                  const double *__restrict__ vel4, const float *__restrict__ rel4,
+                  const int32_t *__restrict__ perm, const int32_t *__restrict__ nbr,
+                  const int32_t *__restrict__ cnt, const uint32_t *__restrict__ cell_start,
+                  const sph_status *__restrict__ status, const double *__restrict__ h_orig, int list_fresh,
+                  double fcutsq, int dim, int n_owned, int store, double *__restrict__ vdot, double *__restrict__ udot)
+{
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = gt >> 4, sub = gt & 15;
+    const int ny = g.ncl[1], per = ny * g.ncl[2];
+    const int sides = g.ncl[0] - 2 > 1 ? 2 : 1;
+    uint32_t first = 0, here = 0;
+    if (c < sides * per) {
+        const int side = c >= per ? 1 : 0, rem = c - side * per;
+        const uint32_t code = cell_code(g, side ? g.ncl[0] - 2 : 1, rem % ny, rem / ny);
+        first = cell_start[code];
+        here = cell_start[code + 1] - first;
+    }
+    const int trips = (int)__reduce_max_sync(0xffffffffu, (here + 15u) >> 4);
+    const bool can_skip = list_fresh && !(status->flags & (SPH_F_OUT_OF_BOX | SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE));
+    const double h0 = h_orig[0];
+    const double hinv = 1.0 / h0, c2 = -12.0 * lucy_norm3(h0) * hinv * hinv;
+    for (int tr = 0; tr < trips; ++tr) {
+        const uint32_t k = (uint32_t)sub + 16u * (uint32_t)tr;
+        const bool active = k < here;
+        const int a = active ? (int)(first + k) : 0;
+        double px = 0, py = 0, pz = 0, pm = 0, vx = 0, vy = 0, vz = 0, Ai = 0;
+        int count = 0, orig = 0;
+        bool interior = true;
+        if (active) {
+            load4(pos4 + 4 * (size_t)a, px, py, pz, pm);
+            load4(vel4 + 4 * (size_t)a, vx, vy, vz, Ai);
+            orig = perm[a];
+            count = orig >= n_owned ? 0 : min(cnt[a], K);
+            interior = cell_is_interior(g, __float_as_uint(reinterpret_cast<const float4 *>(rel4)[a].w));
+        }
+        const bool skip = __all_sync(0xffffffffu, interior) && can_skip;
+        const int32_t *row = nbr + (size_t)(a >> 5) * (size_t)K * 32 + (a & 31);
+        ForceAcc f;
+        if (skip) f = force_row<UNIFORM_H, false>(g, pos4, vel4, perm, h_orig, row, (size_t)32, count, orig, a, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
+        else f = force_row<UNIFORM_H, true>(g, pos4, vel4, perm, h_orig, row, (size_t)32, count, orig, a, px, py, pz, vx, vy, vz, Ai, hinv, c2, fcutsq, dim == 2);
+        (void)pm;
+        if (!active || orig >= n_owned) continue;
+        if (store) {
+            vdot[3 * (size_t)orig] = f.ax;
+            vdot[3 * (size_t)orig + 1] = f.ay;
+            vdot[3 * (size_t)orig + 2] = f.az;
+            udot[orig] = f.du;
+        } else {
+            vdot[3 * (size_t)orig] += f.ax;
+            vdot[3 * (size_t)orig + 1] += f.ay;
+            vdot[3 * (size_t)orig + 2] += f.az;
+            udot[orig] += f.du;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ heat conduction (c_forces.pyx:196-239)
 __global__ void __launch_bounds__(kBlock)
 flux_term_kernel(int n, const int32_t *__restrict__ perm, const double *__restrict__ jq,
@@ -1218,6 +1281,18 @@ int64_t sph_nbr_elems(int32_t n, int32_t max_nbrs)
     return (((int64_t)n + 31) / 32) * 32 * (int64_t)max_nbrs;
 }
 
+int64_t sph_group_tab_elems(const sph_grid *g)
+{
+    return g ? sph_tiles::group_tab_elems(g) : 0;
+}
+
+int sph_group_table(const sph_grid *g, const sph_buffers *b, void *stream)
+{
+    if (!g || !b) return SPH_E_BADARG;
+    if (!b->group_tab || sph_tiles::group_tab_elems(g) == 0) return SPH_OK;
+    return sph_tiles::fill_group_table(g, const_cast<uint32_t *>(b->group_tab), (cudaStream_t)stream);
+}
+
 static uint32_t host_pdep(uint32_t v, uint32_t mask)
 {
     uint32_t r = 0;
@@ -1550,6 +1625,18 @@ int sph_force(const sph_grid *g, const sph_buffers *b, const double *d_press, co
     force_kernel<U, L><<<blocks_for((int64_t)b->n * L, kPPBlock), kPPBlock, 0, s>>>(                           \
         *g, b->n, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->status, d_h_orig,        \
         list_fresh, fcutsq, dim, b->n_owned, first_force ? 1 : 0, part, d_vdot, d_udot)
+    if (part == 2 && b->n_owned > 0 && !g->wrap[0] && g->ncl[0] >= 3) {
+        // a slab's boundary layers through the cell table: 16 lanes per cell of the two layers
+        const int64_t lanes = (int64_t)(g->ncl[0] - 2 > 1 ? 2 : 1) * g->ncl[1] * g->ncl[2] * 16;
+#define SPH_LAUNCH_EDGE(U)                                                                                      \
+    force_edge_kernel<U><<<blocks_for(lanes, kPPBlock), kPPBlock, 0, s>>>(                                      \
+        *g, b->max_nbrs, b->pos4, b->vel4, b->rel4, b->perm, b->nbr, b->cnt, b->cell_start, b->status, d_h_orig, \
+        list_fresh, fcutsq, dim, b->n_owned, first_force ? 1 : 0, d_vdot, d_udot)
+        if (h_uniform) SPH_LAUNCH_EDGE(true);
+        else SPH_LAUNCH_EDGE(false);
+#undef SPH_LAUNCH_EDGE
+        return launch_status();
+    }
     if (h_uniform) {
         if (lpp == 1) SPH_LAUNCH_FORCE(true, 1);
         else if (lpp == 2) SPH_LAUNCH_FORCE(true, 2);

@@ -68,6 +68,8 @@ struct TileArgs {
     int dot;                 // 1: dot-product form of the test, 0: difference form (wide cells)
     const int32_t *perm;
     int n_owned;             // > 0: cells of ghosts (original index >= n_owned) get empty rows
+    const uint32_t *tab;     // sph_buffers.group_tab or nullptr: 16 words per group (group_table_kernel)
+    float shift[12];         // (i - 2) * w[d] at [4 d + i]: fp32 frame shift of window layer i
 };
 
 // shared memory of a block: [S32 | I32 | B | Head]
@@ -75,7 +77,6 @@ struct Head {
     uint32_t off[68];        // exclusive scan of cnt (65 used)
     uint32_t start[64];      // first sorted particle of window cell (wz*4 + wy)*4 + wx
     uint32_t cnt[64];
-    float shift[12];         // (i - 2) * w[d] at [4 d + i]: fp32 frame shift of window layer i
     int gc[4];               // local cell coordinates of the group's base cell
     unsigned long long mbar; // SPH_TILE_TMA: transaction barrier of the bulk copies of the window
 };
@@ -100,6 +101,36 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p)
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// Code contribution of cell layer c (before wrapping) of dimension d, or ~0u when the grid has no such layer: the cell
+// code is additive over the dimensions, (block coordinate * block stride) << lbits plus the in-block Morton bits.
+__device__ __forceinline__ uint32_t layer_part(const sph_grid &g, int d, int c)
+{
+    if (c < 0) {
+        if (!g.wrap[d]) return ~0u;
+        c += g.ncl[d];
+    } else if (c >= g.ncl[d]) {
+        if (!g.wrap[d]) return ~0u;
+        c -= g.ncl[d];
+    }
+    const uint32_t stride = d == 0 ? 1u : (d == 1 ? g.nblk[0] : g.nblk[0] * g.nblk[1]);
+    return ((((uint32_t)c >> g.lb[d]) * stride) << g.lbits) | pdep32((uint32_t)c & ((1u << g.lb[d]) - 1u), g.mask[d]);
+}
+
+// What a block needs to know about its group and depends on the grid only: word 4 d + i of a group's 16 is the code
+// contribution of window layer i of dimension d, words 12..14 the cell coordinates of its base cell.
+__global__ void __launch_bounds__(256)
+group_table_kernel(const __grid_constant__ sph_grid g, uint32_t *__restrict__ tab)
+{
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x, grp = gt >> 4, l = gt & 15u;
+    if (grp >= g.ncode / 8u) return;
+    int cc[3];
+    cell_coords(g, grp * 8u, cc[0], cc[1], cc[2]);
+    uint32_t out = 0u;
+    if (l < 12u) out = layer_part(g, (int)(l >> 2), cc[l >> 2] + (int)(l & 3u) - 1);
+    else if (l < 15u) out = (uint32_t)cc[l - 12u];
+    tab[gt] = out;
+}
+
 // ------------------------------------------------------------------ window of a group
 // Fills Head (window cells, their scan, frame shifts, base coordinates) and stages the window:
 // S32 = fp32 position in the group's frame + its squared norm, I32 = sorted index.  Returns the number of
@@ -116,22 +147,19 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
         // in-block Morton bits.  Lane 4 d + i works out the contribution of window layer i of dimension d;
         // the 64 cell codes are then three shuffles and two adds each, two cells (2 t, 2 t + 1) per lane.
         uint32_t part = ~0u;
-        const int d = (t >> 2) % 3, i = t & 3;
-        uint32_t bx, by, bz;
-        block_coords(g, c0 >> g.lbits, bx, by, bz);
-        const int ccd = (int)(((d == 0 ? bx : (d == 1 ? by : bz)) << g.lb[d]) | pext32(c0, g.mask[d]));
-        if (t < 12) {
-            int c = ccd + i - 1;
-            bool ok = true;
-            if (c < 0) {
-                if (g.wrap[d]) c += g.ncl[d]; else ok = false;
-            } else if (c >= g.ncl[d]) {
-                if (g.wrap[d]) c -= g.ncl[d]; else ok = false;
-            }
-            if (ok) {
-                const uint32_t stride = d == 0 ? 1u : (d == 1 ? g.nblk[0] : g.nblk[0] * g.nblk[1]);
-                part = ((((uint32_t)c >> g.lb[d]) * stride) << g.lbits) |
-                       pdep32((uint32_t)c & ((1u << g.lb[d]) - 1u), g.mask[d]);
+        if (a.tab) {
+            // (one 64-byte row of the per-grid table instead of ~150 dependent integer instructions)
+            const uint32_t v = t < 16 ? a.tab[2u * c0 + (uint32_t)t] : 0u;
+            if (t < 12) part = v;
+            else if (t < 15) H->gc[t - 12] = (int)v;
+        } else {
+            const int d = (t >> 2) % 3, i = t & 3;
+            uint32_t bx, by, bz;
+            block_coords(g, c0 >> g.lbits, bx, by, bz);
+            const int ccd = (int)(((d == 0 ? bx : (d == 1 ? by : bz)) << g.lb[d]) | pext32(c0, g.mask[d]));
+            if (t < 12) {
+                part = layer_part(g, d, ccd + i - 1);
+                if (i == 0) H->gc[d] = ccd;
             }
         }
         uint32_t st[2], cn[2];
@@ -146,11 +174,6 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
                 st[j] = a.cell_start[code];
                 cn[j] = a.cell_start[code + 1];
             }
-        }
-        // (while the four loads are in flight)
-        if (t < 12) {
-            if (i == 0) H->gc[d] = ccd;
-            H->shift[t] = (float)((double)(i - 2) * g.w[d]);
         }
         const uint32_t v0 = cn[0] - st[0], v1 = cn[1] - st[1];
         uint32_t inc = v0 + v1;
@@ -200,7 +223,7 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
     for (int pass = 0; pass < 2; ++pass) {
         const int wc = w * 8 + pass * 4 + (lane >> 3);
         const uint32_t st = H->start[wc], cn = H->cnt[wc], dst = H->off[wc];
-        const float fx = H->shift[wc & 3], fy = H->shift[4 + ((wc >> 2) & 3)], fz = H->shift[8 + (wc >> 4)];
+        const float fx = a.shift[wc & 3], fy = a.shift[4 + ((wc >> 2) & 3)], fz = a.shift[8 + (wc >> 4)];
         for (uint32_t k = lane & 7; k < cn; k += 8) {
             const float4 p = S32[dst + k];
             const float x = p.x + fx, y = p.y + fy, z = p.z + fz;
@@ -221,7 +244,7 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
         for (int pass = 0; pass < 2; ++pass) {
             const int wc = w * 8 + pass * 4 + (lane >> 3);
             st[pass] = H->start[wc]; cn[pass] = H->cnt[wc]; dst[pass] = H->off[wc];
-            fx[pass] = H->shift[wc & 3]; fy[pass] = H->shift[4 + ((wc >> 2) & 3)]; fz[pass] = H->shift[8 + (wc >> 4)];
+            fx[pass] = a.shift[wc & 3]; fy[pass] = a.shift[4 + ((wc >> 2) & 3)]; fz[pass] = a.shift[8 + (wc >> 4)];
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -566,6 +589,9 @@ TileArgs base_args(const sph_grid *g, const sph_buffers *b)
     a.status = b->status;
     a.perm = b->perm;
     a.n_owned = b->n_owned;
+    a.tab = b->group_tab;
+    for (int d = 0; d < 3; ++d)
+        for (int i = 0; i < 4; ++i) a.shift[4 * d + i] = (float)((double)(i - 2) * g->w[d]);
     a.dot = tile_thresholds(g, &a.thr_out, &a.bw) ? 1 : 0;
     // expected neighbours per particle at the mean density of the local grid: a stream of Q = 2 holds 32 hits.
     // (The owned particles over the owned layers when there are ghosts: the count must not depend on the capacity
@@ -582,14 +608,33 @@ TileArgs base_args(const sph_grid *g, const sph_buffers *b)
 
 namespace sph_tiles {
 
-bool eligible(const sph_grid *g, const sph_buffers *b)
+bool grid_has_groups(const sph_grid *g)
 {
-    const char *e = getenv("SPH_TILES");                 // SPH_TILES=0: general kernel only (tests, A/B timing)
-    if ((e && atoi(e) == 0) || !b->rel4 || !b->pos4 || !b->nbr || !b->cnt) return false;
     for (int d = 0; d < 3; ++d)
         if (g->ncl[d] < 3 || g->lb[d] < 1) return false;
     // the three lowest code bits are one bit of x, y, z: a group of 8 consecutive codes is 2 x 2 x 2 cells
     return (g->mask[0] & 7u) == 1u && (g->mask[1] & 7u) == 2u && (g->mask[2] & 7u) == 4u && (g->ncode % 8u) == 0u;
+}
+
+bool eligible(const sph_grid *g, const sph_buffers *b)
+{
+    const char *e = getenv("SPH_TILES");                 // SPH_TILES=0: general kernel only (tests, A/B timing)
+    if ((e && atoi(e) == 0) || !b->rel4 || !b->pos4 || !b->nbr || !b->cnt) return false;
+    return grid_has_groups(g);
+}
+
+int64_t group_tab_elems(const sph_grid *g)
+{
+    return grid_has_groups(g) ? (int64_t)(g->ncode / 8u) * 16 : 0;
+}
+
+int fill_group_table(const sph_grid *g, uint32_t *tab, cudaStream_t s)
+{
+    const int64_t lanes = group_tab_elems(g);
+    if (lanes == 0) return SPH_OK;
+    group_table_kernel<<<(unsigned)((lanes + 255) / 256), 256, 0, s>>>(*g, tab);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPH_OK : (int)e;
 }
 
 int launch_list(const sph_grid *g, const sph_buffers *b, cudaStream_t s)

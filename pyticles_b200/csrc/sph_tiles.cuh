@@ -19,6 +19,12 @@ bool eligible(const sph_grid *g, const sph_buffers *b);
 // Neighbour pass over cell groups: fills the warp-transposed ELL rows and counts of sph_buffers.
 int launch_list(const sph_grid *g, const sph_buffers *b, cudaStream_t s);
 
+// sph_buffers.group_tab: 16 words per group of 8 cell codes (12 window-layer code contributions, 3 base cell
+// coordinates, 1 spare); geometry only.
+bool grid_has_groups(const sph_grid *g);
+int64_t group_tab_elems(const sph_grid *g);
+int fill_group_table(const sph_grid *g, uint32_t *tab, cudaStream_t s);
+
 }  // namespace sph_tiles
 
 // Tensor-core pre-filter variant of the same pass (sph_tiles_mma.cu; SPH_TILES=2 selects it): same contract.

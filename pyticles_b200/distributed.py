@@ -25,6 +25,7 @@ every rank grows and re-evaluates when any rank overflowed.
 exercise on CPU, with the same buffers and ring protocol); `SlabSphEvaluator` adds the CUDA passes.
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -71,16 +72,17 @@ class SlabDecomposition(object):
         return torch.searchsorted(b, layer, right=True)
 
     # ------------------------------------------------------------------ ring exchange (the data-path collective)
-    def ring_exchange(self, send_left, send_right, recv_left, recv_right):
+    def ring_exchange(self, send_left, send_right, recv_left, recv_right, group=None):
         """send_left goes to the left neighbour, send_right to the right one; recv_left receives what the left
         neighbour sent rightwards, recv_right what the right neighbour sent leftwards.  All four buffers have the
         same fixed size on every rank: one ncclGroup of two sends and two receives, no counts, no host sync.
         With two ranks both neighbours are the same peer; messages are matched in issue order (and by tag on gloo:
         0 travels leftwards, 1 rightwards)."""
-        ops = [dist.P2POp(dist.isend, send_left, self.left, self.group, 0),
-               dist.P2POp(dist.isend, send_right, self.right, self.group, 1),
-               dist.P2POp(dist.irecv, recv_right, self.right, self.group, 0),
-               dist.P2POp(dist.irecv, recv_left, self.left, self.group, 1)]
+        group = self.group if group is None else group
+        ops = [dist.P2POp(dist.isend, send_left, self.left, group, 0),
+               dist.P2POp(dist.isend, send_right, self.right, group, 1),
+               dist.P2POp(dist.irecv, recv_right, self.right, group, 0),
+               dist.P2POp(dist.irecv, recv_left, self.left, group, 1)]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
 
@@ -203,7 +205,8 @@ class SlabSphEvaluator(object):
         self._events = []
         self._nvalid = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._halo_buf = None
-        self.overlap_b = False
+        self.overlap_b = os.environ.get("SPH_OVERLAP_B", "0") == "1"
+        self._group_hp = None
         if self.dec.world > 1:
             if halo_cap is None:
                 # a boundary layer holds n_owned / owned layers particles on average
@@ -450,10 +453,13 @@ class SlabSphEvaluator(object):
                 done_b = torch.cuda.Event()
                 done_b.record(side)
             be.force(p, rho, self.h_global, True, self.fcut, 3, vdot, udot, reuse_press=True, first_force=True, part=1)
+            mark("force, all but the boundary layers (exchange B beside it)")
             if timed:
                 ev[6].record()
             main.wait_event(done_b)
+            mark("wait for exchange B")
             be.force(p, rho, self.h_global, True, self.fcut, 3, vdot, udot, reuse_press=True, first_force=True, part=2)
+            mark("force, boundary layers")
         else:
             if multi:                                                                          # B
                 self._exchange_b(L, idx, sb, rb, cap, no, p, rho, stat, st, mark)
@@ -477,7 +483,7 @@ class SlabSphEvaluator(object):
             from_l, from_r = self._peer_exchange("b", sb[0], sb[1])
             mark("B: peer copies + signals")
         else:
-            self.dec.ring_exchange(sb[0], sb[1], rb[0], rb[1])
+            self.dec.ring_exchange(sb[0], sb[1], rb[0], rb[1], group=self._group_hp if self.overlap_b else None)
             mark("B: ring send/recv")
             from_l, from_r = rb[0], rb[1]
         _lib.check(L.sph_halo_unpack2(_P(from_l), _P(from_r), cap, no, _P(p), _P(rho), stat, st), "sph_halo_unpack2")
@@ -486,8 +492,16 @@ class SlabSphEvaluator(object):
         mark("B: ghost pressure term")
 
     def _side_stream(self):
+        if self._group_hp is None and self.device.type == "cuda":
+            # (COLLECTIVE, once: every rank runs the same evaluate().)  NCCL's own stream has to be a high-priority one
+            # too, or the send/recv kernel queues behind the blocks of the force pass.
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            ranks = dist.get_process_group_ranks(self.dec.group) if self.dec.group is not None else None
+            self._group_hp = dist.new_group(ranks=ranks, pg_options=opts)
         if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            # high priority: its few small blocks (pack, the NCCL send/recv kernel, unpack) must get SMs while the force
+            # pass still has hundreds of thousands of blocks queued -- at equal priority they ran AFTER it (measured)
+            self._side = torch.cuda.Stream(device=self.device, priority=-1)
         return self._side
 
     def check(self, _depth=0):

@@ -10,6 +10,7 @@ import os
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import c_oracle as C
 from oracle import oracle as O
@@ -265,3 +266,29 @@ def test_random_geometries_tile_and_general_kernels_agree():
             kinds_checked.add(kind)
             assert np.array_equal(a, C.build_pairs(r, np.array(box), cutoff, tol).astype(np.int64)), (case, kind)
     assert n_tile >= 25            # the tile kernel is the one that ran in most cases
+
+
+def test_blocks_work_out_their_window_without_the_group_table():
+    """sph_buffers.group_tab is optional: with NULL every block of the cell-group kernel derives the cell codes of its
+    window itself (the path a caller that never calls sph_group_table gets).  Same rows, bit for bit."""
+    from pyticles_b200 import neighbour_list
+    r, v, box = O.lattice_workload(22, 14, 18, seed=77, jitter=0.3)       # odd layer counts: half-empty last groups
+    n = r.shape[0]
+    with tiles(True):
+        p = make_system(r, np.zeros_like(r), np.ones(n), np.full(n, 2.0), np.ones(n), box)
+        nl = neighbour_list.VerletList(p, cutoff=2.0, tolerance=0.0)
+        nl.build()
+        be = nl.backend
+        assert be.buf.group_tab, "the backend allocates the table for a grid with cell groups"
+        assert not fallback_flag(nl)
+        with_tab = (be.t["nbr"].clone(), be.t["cnt"].clone())
+        be.buf.group_tab = None
+        be.t["nbr"].zero_()
+        be.t["cnt"].zero_()
+        be.nlist()
+        torch.cuda.synchronize()
+        assert not fallback_flag(nl)
+        assert torch.equal(be.t["cnt"], with_tab[1])
+        assert torch.equal(be.t["nbr"], with_tab[0])
+    ref = C.build_pairs(r, np.array(box), 2.0, 0.0).astype(np.int64)
+    assert np.array_equal(_np(nl.iap).astype(np.int64), ref)
