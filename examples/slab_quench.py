@@ -68,15 +68,17 @@ def main():
         no = sim.n_owned
         S = sim.S
         moved = no - int(torch.isin(sim.own_gid, before).sum())
-        acc = torch.tensor([float(no), float(S["t"][:no].sum()), float(moved)], dtype=torch.float64, device=dev)
+        bad = float(torch.isnan(S["r"][:no]).any())
+        acc = torch.tensor([float(no), float(S["t"][:no].sum()), float(moved), bad], dtype=torch.float64, device=dev)
         lo = S["rho"][:no].min().reshape(1)
         hi = S["rho"][:no].max().reshape(1)
         if world > 1:
             dist.all_reduce(acc)
             dist.all_reduce(lo, op=dist.ReduceOp.MIN)
             dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        if bool(torch.isnan(S["r"][:no]).any()):
-            print("rank %d: stopping due to nan" % rank)
+        if float(acc[3]) > 0.0:                      # decided by ALL ranks together: nobody is left waiting in a collective
+            if bad:
+                print("rank %d: stopping due to nan" % rank)
             break
         if rank == 0:
             print("%4d  %7.3f  %9d  %.6f  %.4f  %.4f  %d" % (k, time() - t0, int(acc[0]), float(acc[1] / acc[0]),

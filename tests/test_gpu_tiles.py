@@ -288,7 +288,15 @@ def test_blocks_work_out_their_window_without_the_group_table():
         be.nlist()
         torch.cuda.synchronize()
         assert not fallback_flag(nl)
-        assert torch.equal(be.t["cnt"], with_tab[1])
-        assert torch.equal(be.t["nbr"], with_tab[0])
+        assert torch.equal(be.t["cnt"][:n], with_tab[1][:n])
+        # entry k of sorted particle a sits at ((a >> 5) K + k) 32 + (a & 31); slots at k >= cnt[a] are never written
+        K, nw = be.K, (n + 31) // 32
+        cnt = torch.zeros(nw * 32, dtype=torch.int32, device=be.t["cnt"].device)
+        cnt[:n] = be.t["cnt"][:n]
+        live = torch.arange(K, device=cnt.device)[None, :, None] < cnt.view(nw, 1, 32)
+        rows_a = be.t["nbr"][:nw * K * 32].view(nw, K, 32)
+        rows_b = with_tab[0][:nw * K * 32].view(nw, K, 32)
+        assert int(live.sum()) == 2 * _np(nl.iap).shape[0]
+        assert torch.equal(rows_a[live], rows_b[live])
     ref = C.build_pairs(r, np.array(box), 2.0, 0.0).astype(np.int64)
     assert np.array_equal(_np(nl.iap).astype(np.int64), ref)
