@@ -1247,17 +1247,18 @@ int lanes_per_particle()
     return lpp;
 }
 
-int g_sm_count = 0;
-
+// per device: one process may drive several GPUs
 int sm_count()
 {
-    if (!g_sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
+    static int sm_of[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev >= 0 && dev < 64 ? dev : 0;
+    if (!sm_of[slot]) {
+        cudaDeviceGetAttribute(&sm_of[slot], cudaDevAttrMultiProcessorCount, dev);
+        if (sm_of[slot] <= 0) sm_of[slot] = 148;
     }
-    return g_sm_count;
+    return sm_of[slot];
 }
 
 constexpr double kCellTarget = 8.0;    // particles per cell the planner widens sparse grids towards (0: off)
@@ -1538,12 +1539,15 @@ int sph_gather(const sph_grid *g, const sph_buffers *b, const double *d_r, const
 
 static int nlist_general(const sph_grid *g, const sph_buffers *b, int only_fallback, cudaStream_t s)
 {
-    static bool configured = false;
+    static bool configured[64] = {};                     // the attribute belongs to the function ON a device
     const size_t smem = sizeof(float4) * kNlWin * kNlWarps;
-    if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = dev >= 0 && dev < 64 ? dev : 0;
+    if (!configured[slot]) {
         cudaFuncSetAttribute(nlist_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(nlist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
+        configured[slot] = true;
     }
     const bool small = g->ncl[0] < 3 || g->ncl[1] < 3 || g->ncl[2] < 3;
     const int64_t warps_needed = g->ncode;

@@ -325,6 +325,7 @@ class SlabSphEvaluator(object):
     def migrate(self):
         """Re-home owned particles whose cell layer changed owner (call after integration)."""
         self._load_rows(self.dec.migrate(self.rows()))
+        self.check_uniform_h()                                # arrivals carry their own h
 
     def check_uniform_h(self):
         """The slab passes use one smoothing length for every pair (h_uniform): refuse anything else, on every
