@@ -3,7 +3,10 @@
 // One block works on a GROUP of 2 x 2 x 2 cells (eight consecutive block-Morton codes), one warp
 // per cell.  The block stages the 4 x 4 x 4 cells around the group ONCE in shared memory as fp32
 // positions in the group's frame (origin at the corner the eight cells share) with their squared norm, so a
-// particle row is read from L2 8x instead of 27x, with coalesced loads.
+// particle row is read from L2 8x instead of 27x, with coalesced loads.  The head of a block -- which 64 cells, how
+// many particles each, where they go -- is ONE warp's work behind ONE barrier: a 64-byte row of the per-grid group
+// table (sph_buffers.group_tab: the cell-code contributions of the 4 + 4 + 4 window layers; geometry only), three
+// shuffles per cell code, the cell_start loads, a warp scan.
 //
 // A warp takes the particles of its cell up to 16 at a time.  Inside a pass, lane = q * P + p:
 // particle p (of P) and candidate stream q of Q = 32 / P.  A lane walks every Q-th candidate of the 9 window columns (3 cells each, contiguous in the
@@ -16,8 +19,8 @@
 // every other pass and the export use).
 //
 // Exactness is the one of the general kernel: d < -bw accepts, d >= 0 rejects (rsq32 >= thr_out), a lane that saw
-// |d| < bw (the rigorous fp32 error band, tile_thresholds) re-decides all its hits with the reference's fp64
-// predicate (pair_exact).  Cases outside the fixed capacities (> 64 particles in a cell, > 32 hits in one stream's
+// |d| < bw (the rigorous fp32 error band, tile_thresholds) works d out again for each of its hits and re-decides
+// those inside the band with the reference's fp64 predicate (pair_exact).  Cases outside the fixed capacities (> 64 particles in a cell, > 32 hits in one stream's
 // list even at Q >= 4, > 1024 particles in the 64 cells of a window, positions far outside the box) raise
 // SPH_F_TILE_FALLBACK and the general kernel redoes the pass.
 //
@@ -26,7 +29,11 @@
 // walking the masks keeps a third of the lanes busy: 5.4 ms), the pass body compiled per Q so that every stride is an
 // immediate (11 % fewer instructions, but four copies of the unrolled column code miss the instruction cache: 4.9 ms),
 // and a tensor-core pre-filter (sph_tiles_mma.cu, SPH_TILES=2: 5.7 ms).  What stayed is the dot-product form of the
-// test with one copy of the pass: 4.26 ms against r1's 4.37.
+// test with one copy of the pass: 4.26 ms against r1's 4.37.  The larger step came from the warp-state samples
+// (profiles/summarise.py stalls): a third of them sat at barriers and on the long scoreboard, i.e. in serial latencies
+// around the tests -- three barrier-separated head phases behind ~250 dependent integer instructions, one window row
+// per loop trip, a status read before every warp's exit, every hit of a lane re-decided in fp64 when one candidate
+// fell into the band.  Taking those out (see the head above, tile_stage, tile_pass, the kernel's last lines): 3.54 ms.
 //
 // Reference semantics (file:line into the reference tree):
 //   pair predicate     neighbour_list.py:105-123,170-178
@@ -51,7 +58,7 @@ constexpr int kTStep = 32 * 2;       // bytes between consecutive hits of a lane
 #ifndef SPH_TILE_BLOCKS
 #define SPH_TILE_BLOCKS 5
 #endif
-constexpr int kTBlocks = SPH_TILE_BLOCKS;   // resident blocks per SM (39 KB of shared memory; 5: 48 registers)
+constexpr int kTBlocks = SPH_TILE_BLOCKS;   // resident blocks per SM (38 KB of shared memory; 5: 48 registers)
 
 constexpr uint32_t kFull = 0xffffffffu;
 
