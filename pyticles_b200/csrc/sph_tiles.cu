@@ -12,15 +12,16 @@
 // particle p (of P) and candidate stream q of Q = 32 / P.  A lane walks every Q-th candidate of the 9 window columns (3 cells each, contiguous in the
 // staged window) around its cell and keeps its own list of hits -- no ballot, no popc, one predicated shared
 // store per hit.  One test is the dot-product form
-//     d = |c|^2 + (|p|^2 - thr_out) - 2 c.p        1 FADD + 3 FFMA  (|c|^2 staged with the position, -2p per lane)
-// with a running minimum of |d| for the error band: 8 instructions with the LDS.128 and the hit bookkeeping
-// (r1: 12 with three subtractions, a multiply, two FFMA and a maximum of the accepted rsq).  The Q lists of a
+//     |c|^2 - 2 c.p  <  thr_out - |p|^2             3 FFMA + FSETP  (|c|^2 staged with the position, -2p and the
+//                                                    right-hand side per lane)
+// and, on a hit, the predicated store, pointer bump and running maximum for the error band: 7 instructions with the
+// LDS.128 (r1: 12 with three subtractions, a multiply, two FFMA and a maximum of the accepted rsq).  The Q lists of a
 // particle are then concatenated, in a fixed order, into its warp-transposed ELL row (the neighbour structure
 // every other pass and the export use).
 //
-// Exactness is the one of the general kernel: d < -bw accepts, d >= 0 rejects (rsq32 >= thr_out), a lane that saw
-// |d| < bw (the rigorous fp32 error band, tile_thresholds) works d out again for each of its hits and re-decides
-// those inside the band with the reference's fp64 predicate (pair_exact).  Cases outside the fixed capacities (> 64 particles in a cell, > 32 hits in one stream's
+// Exactness is the one of the general kernel: rsq32 >= thr_out rejects, rsq32 < thr_out - bw accepts (bw: the
+// rigorous fp32 error band, tile_thresholds); a lane one of whose hits fell between the two works the test value out
+// again for each of its hits and re-decides those inside the band with the reference's fp64 predicate (pair_exact).  Cases outside the fixed capacities (> 64 particles in a cell, > 32 hits in one stream's
 // list even at Q >= 4, > 1024 particles in the 64 cells of a window, positions far outside the box) raise
 // SPH_F_TILE_FALLBACK and the general kernel redoes the pass.
 //
@@ -70,7 +71,7 @@ struct TileArgs {
     int32_t *nbr;
     int32_t *cnt;
     sph_status *status;
-    float thr_out, bw;       // d = rsq32 - thr_out; hits with d >= -bw are settled in fp64
+    float thr_out, bw;       // hit: rsq32 < thr_out; hits with rsq32 >= thr_out - bw are settled in fp64
     int pass0;               // particles of a cell per pass to start with (16 or 8)
     int dot;                 // 1: dot-product form of the test, 0: difference form (wide cells)
     const int32_t *perm;
@@ -81,7 +82,8 @@ struct TileArgs {
 
 // shared memory of a block: [S32 | I32 | B | Head]
 struct Head {
-    uint32_t off[68];        // exclusive scan of cnt (65 used)
+    uint32_t off[68];        // exclusive scan of cnt (65 used; [65]: is there a particle in the group's own cells)
+    uint32_t offb[68];       // the same as shared byte addresses of the staged candidates (S32 + 16 off)
     uint32_t start[64];      // first sorted particle of window cell (wz*4 + wy)*4 + wx
     uint32_t cnt[64];
     int gc[4];               // local cell coordinates of the group's base cell
@@ -196,7 +198,9 @@ __device__ __forceinline__ uint32_t tile_stage(const sph_grid &g, uint32_t c0, c
         *reinterpret_cast<uint2 *>(&H->start[2 * t]) = make_uint2(st[0], st[1]);
         *reinterpret_cast<uint2 *>(&H->cnt[2 * t]) = make_uint2(v0, v1);
         *reinterpret_cast<uint2 *>(&H->off[2 * t]) = make_uint2(ex, ex + v0);
-        if (t == 31) { H->off[64] = inc; H->off[65] = any ? 1u : 0u; }
+        const uint32_t s32a = smem_u32(S32);
+        *reinterpret_cast<uint2 *>(&H->offb[2 * t]) = make_uint2(s32a + 16u * ex, s32a + 16u * (ex + v0));
+        if (t == 31) { H->off[64] = inc; H->off[65] = any ? 1u : 0u; H->offb[64] = s32a + 16u * inc; }
     }
     __syncthreads();
     const uint32_t total = H->off[64];
@@ -306,26 +310,32 @@ __device__ __forceinline__ HomeCell home_cell(const sph_grid &g, const Head *H, 
 #define SPH_LDS4(X, Y, Z, W, ADDR) \
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(X), "=f"(Y), "=f"(Z), "=f"(W) : "r"(ADDR))
 
-// One candidate against one home particle: d = rsq32 - thr_out in the dot-product form.  A hit (d < 0) is kept as
-// the 16-bit shared address of the staged candidate; the band [-bw, 0) is settled by the caller from `near`.
-// SELF: the column holds the particle itself.
-// DOT: the dot-product form, (px2, py2, pz2, Kp) = (-2 p, |p|^2 - thr_out).  Its rounding error grows with the SQUARE of the
-// coordinates, so grids with a cell much wider than the list radius in some dimension (a sheet in a deep box: coarse z
-// cells) take the difference form instead, (px2, py2, pz2, Kp) = (p, -thr_out): three subtractions and three FFMA.
-template <bool DOT, bool CHECK, bool SELF>
-__device__ __forceinline__ void test_one(uint32_t ptr, uint32_t selfptr, float px2, float py2, float pz2, float Kp,
-                                         float cx, float cy, float cz, float cn, uint32_t &lp, uint32_t lp_lim,
-                                         float &near, bool &over)
+// The quantity a candidate is judged by, against the home particle's threshold T:
+// DOT    d = |c|^2 - 2 c.p against T = thr_out - |p|^2, (px2, py2, pz2) = -2 p: three FFMA on the staged (c, |c|^2).  Its
+//        rounding error grows with the SQUARE of the coordinates, so grids with a cell much wider than the list radius in
+//        some dimension (a sheet in a deep box: coarse z cells) take
+// !DOT   d = |c - p|^2 against T = thr_out, (px2, py2, pz2) = p: three subtractions, a multiply and two FFMA.
+template <bool DOT>
+__device__ __forceinline__ float test_value(float px2, float py2, float pz2, float cx, float cy, float cz, float cn)
 {
-    float d;
-    if (DOT) {
-        d = fmaf(cz, pz2, fmaf(cy, py2, fmaf(cx, px2, cn + Kp)));
-    } else {
-        const float dx = cx - px2, dy = cy - py2, dz = cz - pz2;
-        d = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, Kp)));
-    }
-    near = fminf(near, fabsf(d));
-    if (d < 0.f && (!SELF || ptr != selfptr)) {
+    if (DOT) return fmaf(cz, pz2, fmaf(cy, py2, fmaf(cx, px2, cn)));
+    const float dx = cx - px2, dy = cy - py2, dz = cz - pz2;
+    return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
+// One candidate against one home particle.  A hit (d < T, i.e. rsq32 < thr_out) is kept as the 16-bit shared address of
+// the staged candidate; `hmax` follows the largest d among the hits: only a hit with d >= T - bw can lie outside, and
+// the caller settles those in fp64 (a miss needs nothing, however close).  Nothing else happens per test: the
+// comparison takes the threshold as its second operand, so neither it nor the band costs an instruction of its own.
+// SELF: the column holds the particle itself.
+template <bool DOT, bool CHECK, bool SELF>
+__device__ __forceinline__ void test_one(uint32_t ptr, uint32_t selfptr, float px2, float py2, float pz2, float T,
+                                         float cx, float cy, float cz, float cn, uint32_t &lp, uint32_t lp_lim,
+                                         float &hmax, bool &over)
+{
+    const float d = test_value<DOT>(px2, py2, pz2, cx, cy, cz, cn);
+    if (d < T && (!SELF || ptr != selfptr)) {
+        hmax = fmaxf(hmax, d);
         if (CHECK && lp >= lp_lim) {
             over = true;
         } else {
@@ -338,19 +348,19 @@ __device__ __forceinline__ void test_one(uint32_t ptr, uint32_t selfptr, float p
 // One candidate stream (every Q-th candidate from ptr on, below pend; step = 16 Q) of one window column, two per trip
 template <bool DOT, bool CHECK, bool SELF>
 __device__ __forceinline__ void test_column(uint32_t ptr, uint32_t pend, uint32_t step, uint32_t selfptr, float px2,
-                                            float py2, float pz2, float Kp, uint32_t &lp, uint32_t lp_lim, float &near,
+                                            float py2, float pz2, float T, uint32_t &lp, uint32_t lp_lim, float &hmax,
                                             bool &over)
 {
     float ax, ay, az, an, bx, by, bz, bn;
     for (; ptr + step < pend; ptr += 2u * step) {                        // two loads in flight
         SPH_LDS4(ax, ay, az, an, ptr);
         SPH_LDS4(bx, by, bz, bn, ptr + step);
-        test_one<DOT, CHECK, SELF>(ptr, selfptr, px2, py2, pz2, Kp, ax, ay, az, an, lp, lp_lim, near, over);
-        test_one<DOT, CHECK, SELF>(ptr + step, selfptr, px2, py2, pz2, Kp, bx, by, bz, bn, lp, lp_lim, near, over);
+        test_one<DOT, CHECK, SELF>(ptr, selfptr, px2, py2, pz2, T, ax, ay, az, an, lp, lp_lim, hmax, over);
+        test_one<DOT, CHECK, SELF>(ptr + step, selfptr, px2, py2, pz2, T, bx, by, bz, bn, lp, lp_lim, hmax, over);
     }
     if (ptr < pend) {
         SPH_LDS4(ax, ay, az, an, ptr);
-        test_one<DOT, CHECK, SELF>(ptr, selfptr, px2, py2, pz2, Kp, ax, ay, az, an, lp, lp_lim, near, over);
+        test_one<DOT, CHECK, SELF>(ptr, selfptr, px2, py2, pz2, T, ax, ay, az, an, lp, lp_lim, hmax, over);
     }
 }
 
@@ -363,7 +373,7 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
                                               const uint32_t *I32, entry_t *B, const uint32_t *offh, uint32_t c0,
                                               uint32_t cs, int P, int Q, int lane)
 {
-    const uint32_t step = (uint32_t)Q * 16u, qmagic = (65536u + (uint32_t)Q - 1u) / (uint32_t)Q;
+    const uint32_t step = (uint32_t)Q * 16u;
     const int q = (int)(((float)lane + 0.5f) * __frcp_rn((float)P));     // lane / P: never within 1/64 of an integer
     const int p = lane - q * P;
     const bool active = q < Q;
@@ -371,48 +381,42 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
     const uint32_t s32a = smem_u32(S32), s16 = s32a & 0xffffu, selfptr = s32a + selfc * 16u;
     const float4 hp = S32[selfc];
     const float px2 = DOT ? -2.0f * hp.x : hp.x, py2 = DOT ? -2.0f * hp.y : hp.y, pz2 = DOT ? -2.0f * hp.z : hp.z,
-                Kp = DOT ? hp.w - a.thr_out : -a.thr_out;
-    const uint32_t lp0 = smem_u32(B), lp_lim = lp0 + (uint32_t)kTStep * kTRow;
+                T = DOT ? a.thr_out - hp.w : a.thr_out, Tsure = T - a.bw;
+    const uint32_t lp0 = smem_u32(B), lp_lim = lp0 + (uint32_t)kTStep * kTRow, q16 = (uint32_t)q * 16u;
     uint32_t lp = lp0;
-    float near = INFINITY;
+    float hmax = -INFINITY;
     bool over = false;
     if (active) {
 #pragma unroll
         for (int col = 0; col < 9; ++col) {                              // unrolled: 4.43 ms against 4.55 ms as a loop
-            const uint32_t s = offh[((col / 3) * 4 + col % 3) * 4], e = offh[((col / 3) * 4 + col % 3) * 4 + 3];
-            const uint32_t pend = s32a + e * 16u, pbeg = s32a + (s + (uint32_t)q) * 16u;
-            // this lane tests at most (e - s) / Q + 1 candidates of the column ((x * qmagic) >> 16 == x / Q here): with room for that many hits the
-            // loop needs no capacity test
-            const bool room = lp + (uint32_t)kTStep * ((((e - s) * qmagic) >> 16) + 1u) <= lp_lim;
+            // (byte addresses of the column's first candidate and of its end)
+            const uint32_t sb = offh[((col / 3) * 4 + col % 3) * 4], pend = offh[((col / 3) * 4 + col % 3) * 4 + 3];
+            const uint32_t pbeg = sb + q16;
+            // this lane tests at most n / Q + 1 <= n / 2 + 1 of the column's n candidates (Q >= 2): with room for that
+            // many hits (kTStep bytes each: 2 * 16 n + kTStep) the loop needs no capacity test
+            const bool room = lp + ((pend - sb) << 1) + (uint32_t)kTStep <= lp_lim;
             if (col == 4) {                                              // the column that holds the particle itself
-                if (room) test_column<DOT, false, true>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
-                else test_column<DOT, true, true>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
+                if (room) test_column<DOT, false, true>(pbeg, pend, step, selfptr, px2, py2, pz2, T, lp, lp_lim, hmax, over);
+                else test_column<DOT, true, true>(pbeg, pend, step, selfptr, px2, py2, pz2, T, lp, lp_lim, hmax, over);
             } else {
-                if (room) test_column<DOT, false, false>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
-                else test_column<DOT, true, false>(pbeg, pend, step, selfptr, px2, py2, pz2, Kp, lp, lp_lim, near, over);
+                if (room) test_column<DOT, false, false>(pbeg, pend, step, selfptr, px2, py2, pz2, T, lp, lp_lim, hmax, over);
+                else test_column<DOT, true, false>(pbeg, pend, step, selfptr, px2, py2, pz2, T, lp, lp_lim, hmax, over);
             }
         }
     }
     if (__any_sync(kFull, over)) return ~0u;
-    // rare: some candidate of this lane lies in the fp32 error band -> the reference's fp64 predicate on all its hits
-    // (`near` also sees the misses just above the threshold, which need nothing: so d is worked out again for every hit of
-    // the lane -- the same operations on the same operands give the same bits -- and only hits inside the band pay the
-    // two fp64 rows from global memory)
-    if (near < a.bw && lp != lp0) {
+    // rare: a hit of this lane lies in the fp32 error band -> d is worked out again for every hit of the lane (the same
+    // operations on the same operands give the same bits) and the hits inside the band are decided by the reference's
+    // fp64 predicate on the fp64 rows
+    if (hmax >= Tsure) {
         const int nl = (int)((lp - lp0) / (uint32_t)kTStep);
         int m = 0;
         for (int k = 0; k < nl; ++k) {
             const entry_t raw = B[k * 32];
             const uint32_t c = (((uint32_t)raw - s16) & 0xffffu) >> 4;
             const float4 cp = S32[c];
-            float d;
-            if (DOT) {
-                d = fmaf(cp.z, pz2, fmaf(cp.y, py2, fmaf(cp.x, px2, cp.w + Kp)));
-            } else {
-                const float dx = cp.x - px2, dy = cp.y - py2, dz = cp.z - pz2;
-                d = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, Kp)));
-            }
-            if (d < -a.bw || pair_exact(g, a.pos4, (int)asorted, (int)I32[c])) B[32 * m++] = raw;
+            const float d = test_value<DOT>(px2, py2, pz2, cp.x, cp.y, cp.z, cp.w);
+            if (d < Tsure || pair_exact(g, a.pos4, (int)asorted, (int)I32[c])) B[32 * m++] = raw;
         }
         lp = lp0 + (uint32_t)kTStep * (uint32_t)m;
     }
@@ -464,7 +468,7 @@ __device__ __forceinline__ uint32_t tile_cell(const sph_grid &g, const TileArgs 
         }
     }
     entry_t *B = Bblock + w * 32 * kTRow + lane;                         // this lane's list of hits: B[32 k]
-    const uint32_t *offh = H->off + (hc.hz * 4 + hc.hy) * 4 + hc.hx;
+    const uint32_t *offh = H->offb + (hc.hz * 4 + hc.hy) * 4 + hc.hx;
     uint32_t wmax = 0;
 
     // Streams per particle: Q = 32 / P (8 at most).  Long rows (the default
