@@ -310,6 +310,16 @@ __device__ __forceinline__ HomeCell home_cell(const sph_grid &g, const Head *H, 
 #define SPH_LDS4(X, Y, Z, W, ADDR) \
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(X), "=f"(Y), "=f"(Z), "=f"(W) : "r"(ADDR))
 
+// Sorted index of the staged candidate whose shared byte address (16 bits: the window lies below 64 KB) a hit list
+// holds: candidate c = (ptr - S32) / 16 has its index at I32 + 4 c = ptr / 4 + (I32 - S32 / 4) -- one shift-and-add
+// (LEA.HI) in front of the load, with i32c = I32 - S32 / 4 in a register.
+__device__ __forceinline__ uint32_t hit_index(uint32_t raw, uint32_t i32c)
+{
+    uint32_t j;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(j) : "r"((raw >> 2) + i32c));
+    return j;
+}
+
 // The quantity a candidate is judged by, against the home particle's threshold T:
 // DOT    d = |c|^2 - 2 c.p against T = thr_out - |p|^2, (px2, py2, pz2) = -2 p: three FFMA on the staged (c, |c|^2).  Its
 //        rounding error grows with the SQUARE of the coordinates, so grids with a cell much wider than the list radius in
@@ -378,7 +388,7 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
     const int p = lane - q * P;
     const bool active = q < Q;
     const uint32_t selfc = c0 + (uint32_t)p, asorted = cs + (uint32_t)p;
-    const uint32_t s32a = smem_u32(S32), s16 = s32a & 0xffffu, selfptr = s32a + selfc * 16u;
+    const uint32_t s32a = smem_u32(S32), selfptr = s32a + selfc * 16u, i32c = smem_u32(I32) - (s32a >> 2);
     const float4 hp = S32[selfc];
     const float px2 = DOT ? -2.0f * hp.x : hp.x, py2 = DOT ? -2.0f * hp.y : hp.y, pz2 = DOT ? -2.0f * hp.z : hp.z,
                 T = DOT ? a.thr_out - hp.w : a.thr_out, Tsure = T - a.bw;
@@ -413,10 +423,10 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
         int m = 0;
         for (int k = 0; k < nl; ++k) {
             const entry_t raw = B[k * 32];
-            const uint32_t c = (((uint32_t)raw - s16) & 0xffffu) >> 4;
-            const float4 cp = S32[c];
-            const float d = test_value<DOT>(px2, py2, pz2, cp.x, cp.y, cp.z, cp.w);
-            if (d < Tsure || pair_exact(g, a.pos4, (int)asorted, (int)I32[c])) B[32 * m++] = raw;
+            float cx, cy, cz, cn;
+            SPH_LDS4(cx, cy, cz, cn, (uint32_t)raw);
+            const float d = test_value<DOT>(px2, py2, pz2, cx, cy, cz, cn);
+            if (d < Tsure || pair_exact(g, a.pos4, (int)asorted, (int)hit_index(raw, i32c))) B[32 * m++] = raw;
         }
         lp = lp0 + (uint32_t)kTStep * (uint32_t)m;
     }
@@ -435,12 +445,13 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
     int k = 0;
     for (; k + 4 <= nw; k += 4) {                                        // four independent look-up chains in flight
         const uint32_t b0 = B[k * 32], b1 = B[k * 32 + 32], b2 = B[k * 32 + 64], b3 = B[k * 32 + 96];
-        const uint32_t j0 = I32[((b0 - s16) & 0xffffu) >> 4], j1 = I32[((b1 - s16) & 0xffffu) >> 4],
-                       j2 = I32[((b2 - s16) & 0xffffu) >> 4], j3 = I32[((b3 - s16) & 0xffffu) >> 4];
+        const uint32_t j0 = hit_index(b0, i32c), j1 = hit_index(b1, i32c), j2 = hit_index(b2, i32c),
+                       j3 = hit_index(b3, i32c);
         erow[k * 32] = (int32_t)j0; erow[(k + 1) * 32] = (int32_t)j1;
         erow[(k + 2) * 32] = (int32_t)j2; erow[(k + 3) * 32] = (int32_t)j3;
     }
-    for (; k < nw; ++k) erow[k * 32] = (int32_t)I32[(((uint32_t)B[k * 32] - s16) & 0xffffu) >> 4];
+#pragma unroll 1
+    for (; k < nw; ++k) erow[k * 32] = (int32_t)hit_index(B[k * 32], i32c);
     if (q == 0) a.cnt[asorted] = tot;
     return (uint32_t)tot;
 }
