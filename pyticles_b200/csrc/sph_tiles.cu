@@ -34,7 +34,8 @@
 // (profiles/summarise.py stalls): a third of them sat at barriers and on the long scoreboard, i.e. in serial latencies
 // around the tests -- three barrier-separated head phases behind ~250 dependent integer instructions, one window row
 // per loop trip, a status read before every warp's exit, every hit of a lane re-decided in fp64 when one candidate
-// fell into the band.  Taking those out (see the head above, tile_stage, tile_pass, the kernel's last lines): 3.54 ms.
+// fell into the band.  Taking those out (see the head above, tile_stage, tile_pass, the kernel's last lines): 3.54 ms;
+// 3.34 ms with the threshold as the comparison's operand and the leaner column set-up.
 //
 // Reference semantics (file:line into the reference tree):
 //   pair predicate     neighbour_list.py:105-123,170-178
