@@ -487,22 +487,28 @@ __device__ __forceinline__ uint32_t tile_cell(const sph_grid &g, const TileArgs 
     // Verlet tolerance gives ~47 neighbours) overflow a stream's list at Q = 2: the launcher then starts at 8
     // particles per pass (Q >= 4); a cell that overflows at 16 is redone at 8, then at 4, before the general kernel
     // is asked.
+    // A pass of P particles costs every lane 1 / Q = 1 / floor(32 / P) of the window: 1/4 for P = 7..8, 1/3 for 9..10,
+    // 1/2 for 11..16.  So at most 10 particles go into one pass and a longer remainder is taken 8 at a time: a cell of 12
+    // costs 1/4 + 1/8 instead of 1/2 -- and the cells above 10 are the ones their block waits for.
     int pass = a.pass0;
+    int p0 = 0;
 #pragma unroll 1
-    for (int p0 = 0; p0 < hc.P; p0 += pass) {
-        const int P = min(pass, hc.P - p0);
+    while (p0 < hc.P) {
+        const int rem = hc.P - p0;
+        const int P = pass > 8 ? (rem <= 10 ? rem : 8) : min(pass, rem);
         const uint32_t c0 = hc.c0 + (uint32_t)p0, cs = hc.cs + (uint32_t)p0;
         const uint32_t r = tile_pass<DOT>(g, a, S32, I32, B, offh, c0, cs, P, P <= 4 ? 8 : 32 / P, lane);
         if (r == ~0u) {
             if (pass > 4) {
                 pass = pass > 8 ? 8 : 4;
-                p0 = -pass;                                              // start the cell again
+                p0 = 0;                                                  // start the cell again
                 continue;
             }
             if (lane == 0) atomicOr(&a.status->flags, SPH_F_TILE_FALLBACK);
             return 0u;
         }
         wmax = max(wmax, r);
+        p0 += P;
         __syncwarp();                                                    // lists are reused by the next pass
     }
     return wmax;
