@@ -565,7 +565,8 @@ tile_list_kernel(const __grid_constant__ sph_grid g, const __grid_constant__ Til
     wmax = __reduce_max_sync(kFull, wmax);
     // (only rows longer than the capacity report their length: a look at status->max_count before every warp's exit
     // is a round trip to L2 during which the block keeps its shared memory)
-    if ((threadIdx.x & 31) == 0 && wmax > (uint32_t)a.K) {
+    if ((threadIdx.x & 31) == 0 && wmax > (uint32_t)a.K &&
+        !(*(volatile uint32_t *)&a.status->flags & (SPH_F_OUT_OF_RANGE | SPH_F_NONFINITE))) {   // (those rows do not count)
         atomicMax(&a.status->max_count, wmax);
         atomicOr(&a.status->flags, SPH_F_NBR_OVERFLOW);
     }
