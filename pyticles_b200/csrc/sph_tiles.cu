@@ -631,6 +631,7 @@ TileArgs base_args(const sph_grid *g, const sph_buffers *b)
     const double np = slab ? (double)b->n_owned : (double)b->n;
     const double expect = vol > 0.0 ? 4.18879 * g->thr * sqrt(g->thr) * np / vol : 0.0;
     a.pass0 = expect > 38.0 ? 8 : kTPass;
+    if (const char *e = getenv("SPH_TILE_PASS0")) a.pass0 = atoi(e) > 0 ? atoi(e) : a.pass0;   // (experiments)
     return a;
 }
 
