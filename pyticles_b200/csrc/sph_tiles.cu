@@ -356,18 +356,22 @@ __device__ __forceinline__ void test_one(uint32_t ptr, uint32_t selfptr, float p
     }
 }
 
-// One candidate stream (every Q-th candidate from ptr on, below pend; step = 16 Q) of one window column, two per trip
+// One candidate stream of one window column: stream q of Q takes the candidate PAIRS 2 q, 2 q + 1 (+ 2 Q, + 4 Q, ...) from
+// the column's start, i.e. ptr, ptr + 16, then ptr + step2 (= 32 Q bytes), ... below pend -- two adjacent candidates per
+// trip.  (Pairs rather than every Q-th candidate: the two rows a stream takes from a cell of eight then share a
+// 128-byte line of the fp64 arrays, and the rows of a particle list its neighbours stream by stream -- the lanes of a
+// cell, which sweep their rows together in the density and force passes, ask L1 for half as many lines.)
 template <bool DOT, bool CHECK, bool SELF>
 __device__ __forceinline__ void test_column(uint32_t ptr, uint32_t pend, uint32_t step, uint32_t selfptr, float px2,
                                             float py2, float pz2, float T, uint32_t &lp, uint32_t lp_lim, float &hmax,
                                             bool &over)
 {
     float ax, ay, az, an, bx, by, bz, bn;
-    for (; ptr + step < pend; ptr += 2u * step) {                        // two loads in flight
+    for (; ptr + 16u < pend; ptr += step) {                              // two loads in flight
         SPH_LDS4(ax, ay, az, an, ptr);
-        SPH_LDS4(bx, by, bz, bn, ptr + step);
+        SPH_LDS4(bx, by, bz, bn, ptr + 16u);
         test_one<DOT, CHECK, SELF>(ptr, selfptr, px2, py2, pz2, T, ax, ay, az, an, lp, lp_lim, hmax, over);
-        test_one<DOT, CHECK, SELF>(ptr + step, selfptr, px2, py2, pz2, T, bx, by, bz, bn, lp, lp_lim, hmax, over);
+        test_one<DOT, CHECK, SELF>(ptr + 16u, selfptr, px2, py2, pz2, T, bx, by, bz, bn, lp, lp_lim, hmax, over);
     }
     if (ptr < pend) {
         SPH_LDS4(ax, ay, az, an, ptr);
@@ -384,7 +388,7 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
                                               const uint32_t *I32, entry_t *B, const uint32_t *offh, uint32_t c0,
                                               uint32_t cs, int P, int Q, int lane)
 {
-    const uint32_t step = (uint32_t)Q * 16u;
+    const uint32_t step = (uint32_t)Q * 32u;                             // a trip: the next pair of this stream
     const int q = (int)(((float)lane + 0.5f) * __frcp_rn((float)P));     // lane / P: never within 1/64 of an integer
     const int p = lane - q * P;
     const bool active = q < Q;
@@ -393,7 +397,7 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
     const float4 hp = S32[selfc];
     const float px2 = DOT ? -2.0f * hp.x : hp.x, py2 = DOT ? -2.0f * hp.y : hp.y, pz2 = DOT ? -2.0f * hp.z : hp.z,
                 T = DOT ? a.thr_out - hp.w : a.thr_out, Tsure = T - a.bw;
-    const uint32_t lp0 = smem_u32(B), lp_lim = lp0 + (uint32_t)kTStep * kTRow, q16 = (uint32_t)q * 16u;
+    const uint32_t lp0 = smem_u32(B), lp_lim = lp0 + (uint32_t)kTStep * kTRow, q16 = (uint32_t)q * 32u;
     uint32_t lp = lp0;
     float hmax = -INFINITY;
     bool over = false;
@@ -403,9 +407,9 @@ __device__ __forceinline__ uint32_t tile_pass(const sph_grid &g, const TileArgs 
             // (byte addresses of the column's first candidate and of its end)
             const uint32_t sb = offh[((col / 3) * 4 + col % 3) * 4], pend = offh[((col / 3) * 4 + col % 3) * 4 + 3];
             const uint32_t pbeg = sb + q16;
-            // this lane tests at most n / Q + 1 <= n / 2 + 1 of the column's n candidates (Q >= 2): with room for that
-            // many hits (kTStep bytes each: 2 * 16 n + kTStep) the loop needs no capacity test
-            const bool room = lp + ((pend - sb) << 1) + (uint32_t)kTStep <= lp_lim;
+            // this lane tests at most n / Q + 2 <= n / 2 + 2 of the column's n candidates (Q >= 2): with room for that
+            // many hits (kTStep bytes each: 2 * 16 n + 2 kTStep) the loop needs no capacity test
+            const bool room = lp + ((pend - sb) << 1) + 2u * (uint32_t)kTStep <= lp_lim;
             if (col == 4) {                                              // the column that holds the particle itself
                 if (room) test_column<DOT, false, true>(pbeg, pend, step, selfptr, px2, py2, pz2, T, lp, lp_lim, hmax, over);
                 else test_column<DOT, true, true>(pbeg, pend, step, selfptr, px2, py2, pz2, T, lp, lp_lim, hmax, over);
