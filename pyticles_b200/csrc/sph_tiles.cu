@@ -9,8 +9,8 @@
 // shuffles per cell code, the cell_start loads, a warp scan.
 //
 // A warp takes the particles of its cell up to 16 at a time.  Inside a pass, lane = q * P + p:
-// particle p (of P) and candidate stream q of Q = 32 / P.  A lane walks every Q-th candidate of the 9 window columns (3 cells each, contiguous in the
-// staged window) around its cell and keeps its own list of hits -- no ballot, no popc, one predicated shared
+// particle p (of P) and candidate stream q of Q = 32 / P.  A lane walks the candidate pairs 2 q, 2 q + 1 of every 2 Q in the 9 window columns (3 cells
+// each, contiguous in the staged window) around its cell and keeps its own list of hits -- no ballot, no popc, one predicated shared
 // store per hit.  One test is the dot-product form
 //     |c|^2 - 2 c.p  <  thr_out - |p|^2             3 FFMA + FSETP  (|c|^2 staged with the position, -2p and the
 //                                                    right-hand side per lane)
